@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the fake-quantization hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sweep] [--train]
+
+A *step* is one pass of the fused uniform fake-quant forward+backward kernel
+(qd_uniform_fwd_bwd, 'complicated' min/max backward) over one 64 Mi-float32
+tensor with s=16 levels and bucket 256 -- the workload BASELINE.json's
+north_star quotes its 70%-of-HBM-peak target on.  Algorithmic traffic is
+16 bytes per element (read x, g; write q, gout).
+
+Printed JSON line (rank 0):
+  value      algorithmic GB/s, inputs resident in HBM, CUDA-event timed, all ranks aggregated
+  e2e        same metric through the host-buffer C-ABI call (pinned host tensors in,
+             host tensors out; H2D + kernel + D2H inside the timed region)
+  roofline   achieved GB/s of the kernel vs the measured HBM copy peak
+  cpu_baseline  the reference's op chain (oracle/torch_chain.py, a port: /root/reference
+             is not on the GPU box) on the host cores, bounded sample
+With N > 1 every rank runs an independent replica (the op does not shard:
+DESIGN.md "Multi-GPU"), timing is the max over ranks.
+
+--impl reference times the reference's CPU implementation of the path
+(the op-chain port) on the host, same metric and unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ELEMS = 1 << 26          # 64 Mi float32
+LEVELS = 16
+BUCKET = 256
+BYTES_PER_ELEM = 16        # x, g read; q, gout written
+MODE_NAME = "minmax"
+CPU_SAMPLE_ELEMS = 1 << 22
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:                      # pragma: no cover - NVML missing
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_port_throughput(n: int, repeats: int, warmup: int):
+    """The reference's CPU path for one fwd+bwd (oracle/torch_chain.py, same torch ops,
+    all host threads).  Returns (GB/s at 16 B/elt, seconds per pass, threads)."""
+    import torch
+    from oracle import torch_chain as T
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g0 = torch.Generator().manual_seed(0)
+    x = torch.randn(n, generator=g0) * 0.05
+    g = torch.randn(n, generator=torch.Generator().manual_seed(1))
+    best = float("inf")
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        T.uniform_fwd(x, LEVELS, BUCKET)
+        T.uniform_bwd_minmax(x, g, LEVELS, BUCKET)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            best = min(best, dt)
+    return n * BYTES_PER_ELEM / best / 1e9, best, threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    gbs, sec, threads = cpu_port_throughput(CPU_SAMPLE_ELEMS, max(1, args.steps), max(1, args.warmup))
+    sample = f"{CPU_SAMPLE_ELEMS} of {N_ELEMS} elements per step (1/16 of the workload), best of {max(1, args.steps)}"
+    print(json.dumps({
+        "impl": "reference", "metric": "fake_quant_fused_fwd_bwd_algorithmic_GBps", "value": round(gbs, 3), "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3 * (N_ELEMS / CPU_SAMPLE_ELEMS), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": f"uniform fake-quant fused forward+backward ({MODE_NAME} backward), one {N_ELEMS}-float32 tensor per GPU, "
+                        f"s={LEVELS}, bucket_size={BUCKET}, {BYTES_PER_ELEM} algorithmic bytes/element",
+            "elements": N_ELEMS, "levels": LEVELS, "bucket_size": BUCKET, "backward": MODE_NAME,
+            "parallelism": f"replicas x{n_gpus} (op does not shard)",
+            "l2_policy": "inputs+outputs are 1 GiB per step, larger than the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweep", action="store_true", help="also print the per-size / per-op table (profiles/)")
+    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from quantized_distillation_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the quantization ops have no CPU implementation")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = N.lib()
+    mode = N.BWD_MINMAX
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    x = torch.randn(N_ELEMS, generator=gen, device=dev) * 0.05
+    g = torch.randn(N_ELEMS, generator=gen, device=dev)
+    q, gout = torch.empty_like(x), torch.empty_like(g)
+    ws = N.workspace(N_ELEMS, BUCKET, dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = N.stream_ptr(dev)
+
+    def step():
+        N.check(lib.qd_uniform_fwd_bwd(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(gout), N_ELEMS, BUCKET, LEVELS, mode, N.ptr(ws),
+                                       ws.numel(), sp))
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / steps
+    per_gpu_gbs = N_ELEMS * BYTES_PER_ELEM / (ms_per_step * 1e-3) / 1e9
+    value = per_gpu_gbs * world
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region)
+    hx = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+    hx.copy_(x)
+    hg = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+    hg.copy_(g)
+    hq = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+    hgo = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        N.check(lib.qd_uniform_fwd_bwd_host(N.ptr(hx), N.ptr(hg), N.ptr(hq), N.ptr(hgo), N_ELEMS, BUCKET, LEVELS, mode, local_rank))
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert torch.equal(hq, q.cpu()), "e2e result differs from the resident-HBM result"
+    e2e_gbs = N_ELEMS * BYTES_PER_ELEM / e2e_s / 1e9 * world
+
+    peak, peak_src = load_peaks()
+    out = {
+        "metric": "fake_quant_fused_fwd_bwd_algorithmic_GBps", "value": round(value, 1), "unit": "GB/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 5),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_gbs, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * N_ELEMS * 4 * world,
+                "d2h_bytes_per_step": 2 * N_ELEMS * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps,
+                "api": "qd_uniform_fwd_bwd_host (pinned host tensors in and out)"},
+        "gpu_launches": steps,
+        "roofline": {"bound": "hbm", "achieved": round(per_gpu_gbs, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(per_gpu_gbs / peak, 4), "frac_of_nominal_8000": round(per_gpu_gbs / 8000.0, 4),
+                     "peak_source": peak_src, "traffic": None,
+                     "kernel": "qd::warp_rows_kernel<OP_UNIFORM, BWD_MINMAX, R=2, VEC>",
+                     "algorithmic_bytes_per_launch": N_ELEMS * BYTES_PER_ELEM},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as f:
+                out["roofline"]["traffic"] = json.load(f).get("uniform_fwd_bwd_minmax_64Mi_dram_bytes")
+        except Exception:
+            pass
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        gbs, sec, threads = cpu_port_throughput(CPU_SAMPLE_ELEMS, 3, 1)
+        out["cpu_baseline"] = {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+                               "sample": f"{CPU_SAMPLE_ELEMS} of {N_ELEMS} elements (1/16), best of 3, oracle/torch_chain.py "
+                                         "(the reference's torch op chain; /root/reference is absent on the GPU box)"}
+    if args.sweep and rank == 0:
+        from tools import sweep
+        out["sweep_file"] = sweep.run(dev)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,117 @@
+"""ctypes binding of libqd_b200.so (C ABI declared in include/qd_b200.h).
+
+There is no CPU implementation behind this module: if the shared library is
+missing, or no CUDA device is present when an op is called, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqd_b200.so")
+
+QD_OK, QD_ERR_INVALID_ARG, QD_ERR_UNSUPPORTED, QD_ERR_CUDA, QD_ERR_WORKSPACE = range(5)
+BWD_STE, BWD_TRUNCATED, BWD_MINMAX = 0, 1, 2
+RULE_NEAREST, RULE_MIDPOINT = 0, 1
+MAX_STAGED_BUCKET = 49152
+
+_p, _i64, _i32, _u64, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/qd_b200.h one to one
+SIGNATURES = {
+    "qd_version": (C.c_int, []),
+    "qd_last_error": (C.c_char_p, []),
+    "qd_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "qd_bucket_geometry": (C.c_int, [_i64, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "qd_workspace_bytes": (_sz, [_i64, _i64]),
+    "qd_scale_down": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _f32, _p, _sz, _p]),
+    "qd_inv_scale_down": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "qd_uniform_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _f32, _i32, _u64, _u64, _p, _sz, _p]),
+    "qd_uniform_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
+    "qd_uniform_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
+    "qd_nonuniform_fwd": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i64, _i64, _p, _f32, _p, _sz, _p]),
+    "qd_nonuniform_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i64, _i64, _p, _sz, _p]),
+    "qd_centroid_index": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i64, _p]),
+    "qd_index_histogram": (C.c_int, [_p, _i64, _i32, _p, _p]),
+    "qd_plan_create": (C.c_int, [C.POINTER(_p), _i32, _p, _p, _p, _p, _i64]),
+    "qd_plan_destroy": (C.c_int, [_p]),
+    "qd_plan_uniform_fwd": (C.c_int, [_p, _p]),
+    "qd_plan_uniform_bwd": (C.c_int, [_p, _p, _i32, _p]),
+    "qd_uniform_fwd_host": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32]),
+    "qd_uniform_fwd_bwd_host": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32]),
+    "qd_selftest_division": (C.c_int, [_i64, _u64, C.POINTER(_i64), _p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Loads libqd_b200.so once; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} not found: build the sm_100a extension first "
+                        "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)      # AttributeError if the ABI and the header drift apart
+                    fn.restype, fn.argtypes = res, args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    """Maps qd_status to the exception type the reference raises for the same
+    condition (ValueError / NotImplementedError, quant_functions.py:22-33,
+    138-139, 230-236, 326-337)."""
+    if rc == QD_OK:
+        return
+    msg = lib().qd_last_error().decode("utf-8", "replace")
+    if rc == QD_ERR_INVALID_ARG:
+        raise ValueError(msg)
+    if rc == QD_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"libqd_b200 error {rc}: {msg}")
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("quantized_distillation_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU implementation of the quantization ops in this package")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_ws = {}
+
+
+def workspace(n: int, bucket: int, device) -> torch.Tensor:
+    """Per (device, stream) scratch buffer, grown on demand."""
+    need = int(lib().qd_workspace_bytes(n, bucket))
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def geometry(n: int, bucket: int):
+    rows, row_len, padded = _i64(), _i64(), _i64()
+    check(lib().qd_bucket_geometry(n, bucket, C.byref(rows), C.byref(row_len), C.byref(padded)))
+    return rows.value, row_len.value, padded.value

@@ -1,0 +1,592 @@
+// qd_api.cu -- host side of libqd_b200.so: argument checking, path selection
+// and the extern "C" entry points declared in include/qd_b200.h.
+//
+// Path selection by row length L (= bucket, or n when bucket is None / n < bucket):
+//     L <= 1024                  warp path   (registers, 1 HBM pass)
+//     L <= QD_MAX_STAGED_BUCKET  block path  (TMA-staged shared memory, 1 HBM pass)
+//     otherwise                  grid path   (two streaming passes)
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "qd_block_path.cuh"
+#include "qd_grid_path.cuh"
+#include "qd_plan.cuh"
+#include "qd_points_grad.cuh"
+#include "qd_warp_path.cuh"
+
+using namespace qd;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define QD_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return fail(QD_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int qd_version(void) { return 100; }
+extern "C" const char* qd_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------ device info
+struct DevInfo {
+    int sms = 0, major = 0, minor = 0;
+    size_t smem_optin = 0;
+};
+static DevInfo g_dev[64];
+static std::mutex g_mu;
+
+static int dev_info(DevInfo** out) {
+    int d = 0;
+    QD_CUDA(cudaGetDevice(&d));
+    if (d < 0 || d >= 64) return fail(QD_ERR_CUDA, "device ordinal %d out of range", d);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev[d].sms == 0) {
+        int v = 0;
+        QD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d)); g_dev[d].sms = v;
+        QD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, d)); g_dev[d].major = v;
+        QD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, d)); g_dev[d].minor = v;
+        QD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, d)); g_dev[d].smem_optin = (size_t)v;
+    }
+    *out = &g_dev[d];
+    return QD_OK;
+}
+
+extern "C" int qd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    if (sm_count) *sm_count = di->sms;
+    if (cc_major) *cc_major = di->major;
+    if (cc_minor) *cc_minor = di->minor;
+    return QD_OK;
+}
+
+// resident CTAs per SM of a kernel, cached per (device, function)
+static std::unordered_map<const void*, int> g_occ;
+template <typename K>
+static int resident_ctas(K kernel, int threads, size_t smem) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const void* key = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(kernel) ^ ((uintptr_t)d << 56) ^ (smem << 20));
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_occ.find(key);
+        if (it != g_occ.end()) return it->second;
+    }
+    int n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_occ[key] = n;
+    return n;
+}
+
+// ------------------------------------------------------------------ geometry / workspace
+extern "C" int qd_bucket_geometry(int64_t n, int64_t bucket, int64_t* rows, int64_t* row_len, int64_t* padded_len) {
+    Geometry g;
+    if (geometry_of(n, bucket, &g)) return fail(QD_ERR_INVALID_ARG, "n must be > 0 and bucket >= 0 (n=%lld bucket=%lld)", (long long)n, (long long)bucket);
+    if (rows) *rows = g.rows;
+    if (row_len) *row_len = g.row_len;
+    if (padded_len) *padded_len = g.rows * g.row_len;
+    return QD_OK;
+}
+
+static constexpr size_t kPointsGradMaxCtas = 148 * 8;
+static size_t points_grad_ws_bytes() { return kPointsGradMaxCtas * 256 * sizeof(double); }
+
+extern "C" size_t qd_workspace_bytes(int64_t n, int64_t bucket) {
+    Geometry g;
+    if (geometry_of(n, bucket, &g)) return 0;
+    size_t bytes = points_grad_ws_bytes();
+    if (g.row_len > QD_MAX_STAGED_BUCKET) {
+        size_t grid = (size_t)(g.rows * grid_chunks_per_row(g)) * sizeof(ChunkPartial) + (size_t)g.rows * sizeof(RowStat) + 256;
+        if (grid > bytes) bytes = grid;
+    }
+    return bytes + 256;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------ launchers
+template <int OP, int BWD, int R, bool VEC>
+static int launch_warp_inst(const Params& P, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    auto kern = warp_rows_kernel<OP, BWD, R, VEC>;
+    const int occ = resident_ctas(kern, kWarpCtaThreads, 0);
+    int64_t need = (P.geo.rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    int64_t cap = (int64_t)di->sms * occ;
+    int grid = (int)(need < cap ? need : cap);
+    kern<<<grid, kWarpCtaThreads, 0, s>>>(P);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+template <int OP, int BWD>
+static int launch_warp(const Params& P, bool vec, cudaStream_t s) {
+    const int64_t L = P.geo.row_len;
+    if (L <= 256) return vec ? launch_warp_inst<OP, BWD, 2, true>(P, s) : launch_warp_inst<OP, BWD, 2, false>(P, s);
+    if (L <= 512) return vec ? launch_warp_inst<OP, BWD, 4, true>(P, s) : launch_warp_inst<OP, BWD, 4, false>(P, s);
+    return vec ? launch_warp_inst<OP, BWD, 8, true>(P, s) : launch_warp_inst<OP, BWD, 8, false>(P, s);
+}
+
+template <int OP, int BWD>
+static int launch_block(const Params& P, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    auto kern = block_rows_kernel<OP, BWD>;
+    const size_t smem = (size_t)P.geo.row_len * sizeof(float);
+    if (smem + 8192 > di->smem_optin) return fail(QD_ERR_UNSUPPORTED, "row of %lld floats does not fit in shared memory", (long long)P.geo.row_len);
+    QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int occ = resident_ctas(kern, kBlockCtaThreads, smem);
+    int64_t cap = (int64_t)di->sms * occ;
+    int grid = (int)(P.geo.rows < cap ? P.geo.rows : cap);
+    kern<<<grid, kBlockCtaThreads, smem, s>>>(P);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+template <int OP, int BWD>
+static int launch_grid(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    const int64_t cpr = grid_chunks_per_row(P.geo);
+    const int64_t items = P.geo.rows * cpr;
+    const size_t need = (size_t)items * sizeof(ChunkPartial) + (size_t)P.geo.rows * sizeof(RowStat);
+    if (ws == nullptr || ws_bytes < need) return fail(QD_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws_bytes);
+    ChunkPartial* partial = reinterpret_cast<ChunkPartial*>(ws);
+    RowStat* rowstat = reinterpret_cast<RowStat*>(partial + items);
+    const int64_t cap = (int64_t)di->sms * 4;
+    const int grid = (int)(items < cap ? items : cap);
+    grid_stats_partial<<<grid, kGridCtaThreads, 0, s>>>(P, partial, cpr, P.argmin != nullptr ? 1 : 0);
+    QD_CUDA(cudaGetLastError());
+    grid_stats_final<<<(int)P.geo.rows, 256, 0, s>>>(P, partial, rowstat, cpr);
+    QD_CUDA(cudaGetLastError());
+    if (OP != OP_STATS) {
+        grid_apply<(OP == OP_STATS ? OP_SCALE : OP), BWD><<<grid, kGridCtaThreads, 0, s>>>(P, rowstat, cpr);
+        QD_CUDA(cudaGetLastError());
+    }
+    return QD_OK;
+}
+
+// true when every row of every non-null float tensor starts 16-byte aligned
+static bool rows_vectorizable(const Params& P) {
+    const bool ptrs = aligned16(P.x) && aligned16(P.g) && aligned16(P.q) && aligned16(P.gout) && aligned16(P.xhat) &&
+                      ((reinterpret_cast<uintptr_t>(P.idx8) & 3) == 0);
+    return ptrs && (P.geo.rows == 1 || (P.geo.row_len % 4) == 0);
+}
+
+template <int OP, int BWD>
+static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
+    if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
+    if (P.geo.row_len <= 1024) return launch_warp<OP, BWD>(P, rows_vectorizable(P), s);
+    if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP, BWD>(P, s);
+    if (BWD == BWD_MINMAX)
+        return fail(QD_ERR_UNSUPPORTED, "minmax backward needs bucket <= %d (reference: bucket_size None not supported, quant_functions.py:332-334)", QD_MAX_STAGED_BUCKET);
+    return launch_grid<OP, (BWD == BWD_MINMAX ? BWD_OFF : BWD)>(P, ws, ws_bytes, s);
+}
+
+static Params blank_params() {
+    Params P;
+    memset(&P, 0, sizeof(P));
+    return P;
+}
+
+// ------------------------------------------------------------------ a2 / a3
+extern "C" int qd_scale_down(const float* x, float* xhat, float* alpha, float* beta, int64_t* argmin, int64_t* argmax,
+                             int64_t n, int64_t bucket, const float* mean, float max_element, void* workspace,
+                             size_t workspace_bytes, qd_stream_t stream) {
+    Params P = blank_params();
+    if (x == nullptr) return fail(QD_ERR_INVALID_ARG, "x is NULL");
+    if ((alpha == nullptr) != (beta == nullptr) || (argmin == nullptr) != (argmax == nullptr))
+        return fail(QD_ERR_INVALID_ARG, "alpha/beta and argmin/argmax must be given in pairs");
+    if (geometry_of(n, bucket, &P.geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry n=%lld bucket=%lld", (long long)n, (long long)bucket);
+    P.x = x; P.xhat = xhat; P.alpha = alpha; P.beta = beta; P.argmin = argmin; P.argmax = argmax;
+    P.mean = mean; P.max_element = max_element;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (xhat == nullptr) return run_rows<OP_STATS, BWD_OFF>(P, workspace, workspace_bytes, s);
+    return run_rows<OP_SCALE, BWD_OFF>(P, workspace, workspace_bytes, s);
+}
+
+__global__ void inv_scale_kernel(const float* __restrict__ y, float* __restrict__ out, const float* __restrict__ alpha,
+                                 const float* __restrict__ beta, const float* __restrict__ mean, Geometry geo) {
+    const float m = mean ? *mean : 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < geo.n; i += stride) {
+        const int64_t row = i / geo.row_len;
+        float v = from_unit(y[i], alpha[row], beta[row]);  // mul_, add_ (quant_functions.py:142-143)
+        if (mean) v = __fadd_rn(v, m);                      // add_(mean) (:148)
+        out[i] = v;
+    }
+}
+
+extern "C" int qd_inv_scale_down(const float* y, float* out, const float* alpha, const float* beta, const float* mean,
+                                 int64_t n, int64_t bucket, qd_stream_t stream) {
+    Geometry g;
+    if (y == nullptr || out == nullptr || alpha == nullptr || beta == nullptr) return fail(QD_ERR_INVALID_ARG, "NULL argument");
+    if (geometry_of(n, bucket, &g)) return fail(QD_ERR_INVALID_ARG, "bad geometry");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    int64_t need = (n + 255) / 256;
+    int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
+    inv_scale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, out, alpha, beta, mean, g);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+// ------------------------------------------------------------------ a4 / a5
+static int uniform_common(Params& P, int64_t n, int64_t bucket, int levels) {
+    if (levels < 2) return fail(QD_ERR_INVALID_ARG, "levels (s) must be >= 2, got %d", levels);
+    if (geometry_of(n, bucket, &P.geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry n=%lld bucket=%lld", (long long)n, (long long)bucket);
+    P.S = (float)(levels - 1);
+    return QD_OK;
+}
+
+extern "C" int qd_uniform_fwd(const float* x, float* q, uint8_t* idx_u8, float* alpha, float* beta, int64_t* argmin,
+                              int64_t* argmax, int64_t n, int64_t bucket, int levels, const float* mean,
+                              float max_element, int stochastic, uint64_t seed, uint64_t offset, void* workspace,
+                              size_t workspace_bytes, qd_stream_t stream) {
+    Params P = blank_params();
+    if (x == nullptr || (q == nullptr && idx_u8 == nullptr)) return fail(QD_ERR_INVALID_ARG, "x and one of q / idx_u8 are required");
+    if ((alpha == nullptr) != (beta == nullptr) || (argmin == nullptr) != (argmax == nullptr))
+        return fail(QD_ERR_INVALID_ARG, "alpha/beta and argmin/argmax must be given in pairs");
+    if (idx_u8 != nullptr && levels > 256) return fail(QD_ERR_INVALID_ARG, "idx_u8 needs levels <= 256");
+    int rc = uniform_common(P, n, bucket, levels);
+    if (rc) return rc;
+    P.x = x; P.q = q; P.idx8 = idx_u8; P.alpha = alpha; P.beta = beta; P.argmin = argmin; P.argmax = argmax;
+    P.mean = mean; P.max_element = max_element; P.stochastic = stochastic; P.seed = seed; P.offset = offset;
+    return run_rows<OP_UNIFORM, BWD_OFF>(P, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int uniform_bwd_dispatch(Params& P, int mode, void* ws, size_t wsb, cudaStream_t s) {
+    switch (mode) {
+        case QD_BWD_STE: return run_rows<OP_UNIFORM, BWD_STE>(P, ws, wsb, s);
+        case QD_BWD_TRUNCATED: return run_rows<OP_UNIFORM, BWD_TRUNC>(P, ws, wsb, s);
+        case QD_BWD_MINMAX:
+            if (P.geo.rows == 1 && P.geo.row_len == P.geo.n && P.geo.n > QD_MAX_STAGED_BUCKET)
+                return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
+            return run_rows<OP_UNIFORM, BWD_MINMAX>(P, ws, wsb, s);
+        default: return fail(QD_ERR_INVALID_ARG, "unknown backward mode %d", mode);
+    }
+}
+
+extern "C" int qd_uniform_bwd(const float* x, const float* g, float* gout, int64_t n, int64_t bucket, int levels,
+                              int mode, void* workspace, size_t workspace_bytes, qd_stream_t stream) {
+    Params P = blank_params();
+    if (x == nullptr || g == nullptr || gout == nullptr) return fail(QD_ERR_INVALID_ARG, "NULL argument");
+    if (mode == QD_BWD_MINMAX && bucket == 0)
+        return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
+    int rc = uniform_common(P, n, bucket, levels);
+    if (rc) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (mode == QD_BWD_STE) {  // grad_input = grad_output
+        if (gout != g) QD_CUDA(cudaMemcpyAsync(gout, g, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return QD_OK;
+    }
+    P.x = x; P.g = g; P.gout = gout;
+    return uniform_bwd_dispatch(P, mode, workspace, workspace_bytes, s);
+}
+
+extern "C" int qd_uniform_fwd_bwd(const float* x, const float* g, float* q, float* gout, int64_t n, int64_t bucket,
+                                  int levels, int mode, void* workspace, size_t workspace_bytes, qd_stream_t stream) {
+    Params P = blank_params();
+    if (x == nullptr || g == nullptr || q == nullptr || gout == nullptr) return fail(QD_ERR_INVALID_ARG, "NULL argument");
+    if (mode == QD_BWD_MINMAX && bucket == 0)
+        return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
+    int rc = uniform_common(P, n, bucket, levels);
+    if (rc) return rc;
+    P.x = x; P.g = g; P.q = q; P.gout = gout;
+    return uniform_bwd_dispatch(P, mode, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ a6 / a7 / a8
+extern "C" int qd_nonuniform_fwd(const float* x, const float* points, int num_points, int rule, float* q,
+                                 uint8_t* idx_u8, int64_t* idx_i64, float* alpha, float* beta, int64_t n,
+                                 int64_t bucket, const float* mean, float max_element, void* workspace,
+                                 size_t workspace_bytes, qd_stream_t stream) {
+    Params P = blank_params();
+    if (x == nullptr || points == nullptr) return fail(QD_ERR_INVALID_ARG, "x and points are required");
+    if (q == nullptr && idx_u8 == nullptr && idx_i64 == nullptr) return fail(QD_ERR_INVALID_ARG, "no output requested");
+    if (num_points < 1 || num_points > 256) return fail(QD_ERR_INVALID_ARG, "num_points must be in [1, 256], got %d", num_points);
+    if (rule != QD_RULE_NEAREST && rule != QD_RULE_MIDPOINT) return fail(QD_ERR_INVALID_ARG, "unknown rule %d", rule);
+    if ((alpha == nullptr) != (beta == nullptr)) return fail(QD_ERR_INVALID_ARG, "alpha/beta must be given in pairs");
+    if (geometry_of(n, bucket, &P.geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry n=%lld bucket=%lld", (long long)n, (long long)bucket);
+    P.x = x; P.q = q; P.idx8 = idx_u8; P.idx64 = idx_i64; P.alpha = alpha; P.beta = beta;
+    P.points = points; P.num_points = num_points; P.rule = rule; P.mean = mean; P.max_element = max_element;
+    return run_rows<OP_NONUNIFORM, BWD_OFF>(P, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int qd_nonuniform_bwd(const float* g, const uint8_t* idx_u8, const int64_t* idx_i64, const float* alpha,
+                                 int num_points, float* grad_points, int64_t n, int64_t bucket, void* workspace,
+                                 size_t workspace_bytes, qd_stream_t stream) {
+    Geometry geo;
+    if (g == nullptr || alpha == nullptr || grad_points == nullptr) return fail(QD_ERR_INVALID_ARG, "NULL argument");
+    if ((idx_u8 == nullptr) == (idx_i64 == nullptr)) return fail(QD_ERR_INVALID_ARG, "exactly one of idx_u8 / idx_i64 must be given");
+    if (num_points < 1 || num_points > 256) return fail(QD_ERR_INVALID_ARG, "num_points must be in [1, 256], got %d", num_points);
+    if (geometry_of(n, bucket, &geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    const int64_t items = geo.rows * ((geo.row_len + kPgItem - 1) / kPgItem);
+    int64_t need_ctas = (items + kPgWarps - 1) / kPgWarps;
+    int64_t cap = (int64_t)di->sms * 8;
+    if (cap > (int64_t)kPointsGradMaxCtas) cap = kPointsGradMaxCtas;
+    const int grid = (int)(need_ctas < cap ? need_ctas : cap);
+    const size_t need = (size_t)grid * num_points * sizeof(double);
+    if (workspace == nullptr || workspace_bytes < need) return fail(QD_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    double* partial = reinterpret_cast<double*>(workspace);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)kPgWarps * num_points * sizeof(double);
+    if (idx_u8)
+        points_grad_partial<uint8_t><<<grid, kPgThreads, smem, s>>>(g, idx_u8, alpha, num_points, geo, partial);
+    else
+        points_grad_partial<int64_t><<<grid, kPgThreads, smem, s>>>(g, idx_i64, alpha, num_points, geo, partial);
+    QD_CUDA(cudaGetLastError());
+    points_grad_final<<<1, 256, 0, s>>>(partial, grid, num_points, grad_points);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+// index search on pre-scaled values (pre-processed path of the reference)
+__global__ void __launch_bounds__(256) centroid_index_kernel(const float* __restrict__ xhat, const float* __restrict__ points,
+                                                            int K, int rule, uint8_t* idx8, int64_t* idx64,
+                                                            float* unit_out, int64_t n) {
+    __shared__ float s_k[256];
+    __shared__ float s_m[256];
+    centroid_setup(s_k, s_m, points, K);
+    __syncthreads();
+    Centroids cen{s_k, s_m, K};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int id = centroid_index(cen, xhat[i], rule);
+        if (idx8) idx8[i] = (uint8_t)id;
+        if (idx64) idx64[i] = id;
+        if (unit_out) unit_out[i] = s_k[id];
+    }
+}
+
+extern "C" int qd_centroid_index(const float* xhat, const float* points, int num_points, int rule, uint8_t* idx_u8,
+                                 int64_t* idx_i64, float* unit_out, int64_t n, qd_stream_t stream) {
+    if (xhat == nullptr || points == nullptr || n <= 0) return fail(QD_ERR_INVALID_ARG, "NULL argument or n <= 0");
+    if (num_points < 1 || num_points > 256) return fail(QD_ERR_INVALID_ARG, "num_points must be in [1, 256], got %d", num_points);
+    if (rule != QD_RULE_NEAREST && rule != QD_RULE_MIDPOINT) return fail(QD_ERR_INVALID_ARG, "unknown rule %d", rule);
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    int64_t need = (n + 255) / 256;
+    int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
+    centroid_index_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xhat, points, num_points, rule, idx_u8,
+                                                                                  idx_i64, unit_out, n);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+// ------------------------------------------------------------------ f2: histogram of indices
+__global__ void __launch_bounds__(256) index_histogram_kernel(const uint8_t* __restrict__ idx, int64_t n, int bins,
+                                                             unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_h[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_h[0][0])[i] = 0u;
+    __syncthreads();
+    unsigned int* h = s_h[threadIdx.x >> 5];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
+    const int64_t nv = vec ? (n >> 4) : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        uint4 w = reinterpret_cast<const uint4*>(idx)[i];
+        unsigned int ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) atomicAdd(&h[(ws[a] >> (8 * b)) & 0xffu], 1u);
+    }
+    for (int64_t i = nv * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&h[idx[i]], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += 256) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += s_h[w][b];
+        if (s) atomicAdd(&counts[b], s);
+    }
+}
+
+extern "C" int qd_index_histogram(const uint8_t* idx_u8, int64_t n, int num_bins, int64_t* counts, qd_stream_t stream) {
+    if (idx_u8 == nullptr || counts == nullptr || n <= 0) return fail(QD_ERR_INVALID_ARG, "NULL argument or n <= 0");
+    if (num_bins < 1 || num_bins > 256) return fail(QD_ERR_INVALID_ARG, "num_bins must be in [1, 256]");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    int64_t need = (n / 16 + 255) / 256 + 1;
+    int grid = (int)(need < (int64_t)di->sms * 4 ? need : (int64_t)di->sms * 4);
+    index_histogram_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        idx_u8, n, num_bins, reinterpret_cast<unsigned long long*>(counts));
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+// ------------------------------------------------------------------ plans (f1)
+struct qd_plan {
+    int count = 0;
+    int64_t bucket = 0;
+    int64_t total_rows = 0;
+    int64_t max_row_len = 0;
+    bool warp_path = true;
+    std::vector<PlanEntry> host;
+    PlanEntry* dev = nullptr;
+    float** dev_grads = nullptr;  // count pointers, refreshed per backward call
+    void* workspace = nullptr;    // for tensors that need the grid path
+    size_t workspace_bytes = 0;
+    int device = 0;
+};
+
+extern "C" int qd_plan_create(qd_plan** out, int count, const float* const* src, float* const* dst, const int64_t* n,
+                              const int32_t* levels, int64_t bucket) {
+    if (out == nullptr || count <= 0 || src == nullptr || dst == nullptr || n == nullptr || levels == nullptr)
+        return fail(QD_ERR_INVALID_ARG, "bad plan arguments");
+    qd_plan* p = new qd_plan();
+    p->count = count;
+    p->bucket = bucket;
+    p->host.resize(count);
+    cudaGetDevice(&p->device);
+    int64_t row = 0;
+    size_t ws = 0;
+    for (int i = 0; i < count; ++i) {
+        Geometry g;
+        if (geometry_of(n[i], bucket, &g) || levels[i] < 2 || src[i] == nullptr || dst[i] == nullptr) {
+            delete p;
+            return fail(QD_ERR_INVALID_ARG, "bad tensor %d in plan (n=%lld levels=%d)", i, (long long)n[i], levels[i]);
+        }
+        PlanEntry& e = p->host[i];
+        e.src = src[i]; e.dst = dst[i]; e.n = n[i]; e.row_start = row; e.rows = g.rows; e.row_len = g.row_len;
+        e.S = (float)(levels[i] - 1);
+        e.vec = (aligned16(src[i]) && aligned16(dst[i]) && (g.rows == 1 || g.row_len % 4 == 0)) ? 1 : 0;
+        row += g.rows;
+        if (g.row_len > p->max_row_len) p->max_row_len = g.row_len;
+        size_t w = qd_workspace_bytes(n[i], bucket);
+        if (w > ws) ws = w;
+    }
+    p->total_rows = row;
+    p->warp_path = p->max_row_len <= 1024;
+    cudaError_t e = cudaMalloc(&p->dev, sizeof(PlanEntry) * count);
+    if (e == cudaSuccess) e = cudaMalloc(&p->dev_grads, sizeof(float*) * count);
+    if (e == cudaSuccess && !p->warp_path) { e = cudaMalloc(&p->workspace, ws); p->workspace_bytes = ws; }
+    if (e == cudaSuccess) e = cudaMemcpy(p->dev, p->host.data(), sizeof(PlanEntry) * count, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        qd_plan_destroy(p);
+        return fail(QD_ERR_CUDA, "plan allocation: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return QD_OK;
+}
+
+extern "C" int qd_plan_destroy(qd_plan* p) {
+    if (p == nullptr) return QD_OK;
+    if (p->dev) cudaFree(p->dev);
+    if (p->dev_grads) cudaFree(p->dev_grads);
+    if (p->workspace) cudaFree(p->workspace);
+    delete p;
+    return QD_OK;
+}
+
+template <int BWD>
+static int plan_launch(const qd_plan* p, float* const* dev_grads, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    int64_t need = (p->total_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+#define QD_PLAN_LAUNCH(RR)                                                                        \
+    {                                                                                             \
+        auto kern = plan_rows_kernel<BWD, RR>;                                                    \
+        int64_t cap = (int64_t)di->sms * resident_ctas(kern, kWarpCtaThreads, 0);                 \
+        int grid = (int)(need < cap ? need : cap);                                                \
+        kern<<<grid, kWarpCtaThreads, 0, s>>>(p->dev, p->count, p->total_rows, dev_grads);        \
+    }
+    if (p->max_row_len <= 256) QD_PLAN_LAUNCH(2)
+    else if (p->max_row_len <= 512) QD_PLAN_LAUNCH(4)
+    else QD_PLAN_LAUNCH(8)
+#undef QD_PLAN_LAUNCH
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_plan_uniform_fwd(const qd_plan* p, qd_stream_t stream) {
+    if (p == nullptr) return fail(QD_ERR_INVALID_ARG, "plan is NULL");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->warp_path) return plan_launch<BWD_OFF>(p, nullptr, s);
+    for (int i = 0; i < p->count; ++i) {  // long rows: per-tensor block / grid path
+        const PlanEntry& e = p->host[i];
+        int rc = qd_uniform_fwd(e.src, e.dst, nullptr, nullptr, nullptr, nullptr, nullptr, e.n, p->bucket, (int)e.S + 1,
+                                nullptr, 0.f, 0, 0, 0, p->workspace, p->workspace_bytes, stream);
+        if (rc) return rc;
+    }
+    return QD_OK;
+}
+
+extern "C" int qd_plan_uniform_bwd(const qd_plan* p, float* const* grad, int mode, qd_stream_t stream) {
+    if (p == nullptr || grad == nullptr) return fail(QD_ERR_INVALID_ARG, "plan or grad is NULL");
+    if (mode == QD_BWD_STE) return QD_OK;  // identity
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!p->warp_path) {
+        for (int i = 0; i < p->count; ++i) {
+            const PlanEntry& e = p->host[i];
+            int rc = qd_uniform_bwd(e.src, grad[i], grad[i], e.n, p->bucket, (int)e.S + 1, mode, p->workspace,
+                                    p->workspace_bytes, stream);
+            if (rc) return rc;
+        }
+        return QD_OK;
+    }
+    QD_CUDA(cudaMemcpyAsync(p->dev_grads, grad, sizeof(float*) * p->count, cudaMemcpyHostToDevice, s));
+    if (mode == QD_BWD_TRUNCATED) return plan_launch<BWD_TRUNC>(p, p->dev_grads, s);
+    if (mode == QD_BWD_MINMAX) {
+        if (p->bucket == 0) return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
+        return plan_launch<BWD_MINMAX>(p, p->dev_grads, s);
+    }
+    return fail(QD_ERR_INVALID_ARG, "unknown backward mode %d", mode);
+}
+
+// ------------------------------------------------------------------ self test
+// Checks the float32 pipeline pieces on device against double arithmetic where
+// double rounding cannot occur: quotient in [0,1] of 24-bit operands.
+__global__ void selftest_division_kernel(int64_t pairs, uint64_t seed, unsigned long long* mismatches) {
+    Philox rng(seed);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+        uint4 r = rng((uint64_t)i);
+        float d = __uint_as_float((r.x & 0x007fffffu) | (((r.y % 60u) + 97u) << 23));  // 2^-30 .. 2^29
+        float frac = u01(r.z);
+        float a = __fmul_rn(d, frac);
+        float q = __fdiv_rn(a, d);
+        double qd = (double)a / (double)d;  // exact to 53 bits; rounding to 24 is then correct
+        float qr = (float)qd;               // unless qd sits within 2^-29 rel. of a tie (never for 24-bit a, d)
+        if (q != qr) atomicAdd(mismatches, 1ull);
+    }
+}
+
+extern "C" int qd_selftest_division(int64_t pairs, uint64_t seed, int64_t* mismatches, qd_stream_t stream) {
+    unsigned long long* d = nullptr;
+    QD_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    QD_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));
+    selftest_division_kernel<<<1184, 256, 0, s>>>(pairs, seed, d);
+    unsigned long long h = 0;
+    QD_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+    QD_CUDA(cudaStreamSynchronize(s));
+    QD_CUDA(cudaFree(d));
+    if (mismatches) *mismatches = (int64_t)h;
+    return QD_OK;
+}

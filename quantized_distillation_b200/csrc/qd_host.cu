@@ -1,0 +1,139 @@
+// qd_host.cu -- host-buffer entry points: what a caller holding CPU tensors
+// gets (the reference's functions accept CPU tensors; here the arithmetic still
+// runs on the GPU).  The tensor is cut into row-aligned chunks and each chunk
+// travels H2D -> fused kernel -> D2H on one of three streams, so the two PCIe
+// directions and the kernel overlap; end-to-end time is bounded by the slower
+// PCIe direction, not by their sum.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include "qd_b200.h"
+
+namespace {
+
+constexpr int kSlots = 3;
+constexpr int64_t kChunkElems = 4 << 20;  // 16 MiB per buffer
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    float *x = nullptr, *g = nullptr, *q = nullptr, *gout = nullptr;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+struct HostCtx {
+    bool ready = false;
+    Slot slot[kSlots];
+    float *big_x = nullptr, *big_g = nullptr, *big_q = nullptr, *big_gout = nullptr;  // bucket=None path
+    int64_t big_cap = 0;
+    void* big_ws = nullptr;
+    size_t big_ws_bytes = 0;
+};
+
+HostCtx g_ctx[64];
+std::mutex g_mu;
+
+int ensure_ctx(int device, HostCtx** out) {
+    if (device < 0 || device >= 64) return QD_ERR_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return QD_ERR_CUDA;
+    HostCtx& c = g_ctx[device];
+    if (!c.ready) {
+        for (int i = 0; i < kSlots; ++i) {
+            Slot& s = c.slot[i];
+            if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return QD_ERR_CUDA;
+            const size_t bytes = (size_t)kChunkElems * sizeof(float);
+            if (cudaMalloc(&s.x, bytes) != cudaSuccess || cudaMalloc(&s.g, bytes) != cudaSuccess ||
+                cudaMalloc(&s.q, bytes) != cudaSuccess || cudaMalloc(&s.gout, bytes) != cudaSuccess)
+                return QD_ERR_CUDA;
+            s.ws_bytes = qd_workspace_bytes(kChunkElems, 0);
+            if (cudaMalloc(&s.ws, s.ws_bytes) != cudaSuccess) return QD_ERR_CUDA;
+        }
+        c.ready = true;
+    }
+    *out = &c;
+    return QD_OK;
+}
+
+int run_host(const float* hx, const float* hg, float* hq, float* hgout, int64_t n, int64_t bucket, int levels, int mode,
+             int device) {
+    if (hx == nullptr || hq == nullptr || n <= 0 || bucket < 0) return QD_ERR_INVALID_ARG;
+    const bool bwd = hg != nullptr;
+    if (bwd && hgout == nullptr) return QD_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(g_mu);
+    HostCtx* c;
+    int rc = ensure_ctx(device, &c);
+    if (rc) return rc;
+
+    int64_t rows, row_len, padded;
+    rc = qd_bucket_geometry(n, bucket, &rows, &row_len, &padded);
+    if (rc) return rc;
+
+    if (row_len > kChunkElems) {
+        // one row spans more than a chunk (bucket None on a large tensor): no row-aligned
+        // cut exists, so stage the whole tensor; copies still run at PCIe rate.
+        if (c->big_cap < n) {
+            cudaFree(c->big_x); cudaFree(c->big_g); cudaFree(c->big_q); cudaFree(c->big_gout); cudaFree(c->big_ws);
+            const size_t bytes = (size_t)n * sizeof(float);
+            c->big_ws_bytes = qd_workspace_bytes(n, bucket);
+            if (cudaMalloc(&c->big_x, bytes) != cudaSuccess || cudaMalloc(&c->big_g, bytes) != cudaSuccess ||
+                cudaMalloc(&c->big_q, bytes) != cudaSuccess || cudaMalloc(&c->big_gout, bytes) != cudaSuccess ||
+                cudaMalloc(&c->big_ws, c->big_ws_bytes) != cudaSuccess) {
+                c->big_cap = 0;
+                return QD_ERR_CUDA;
+            }
+            c->big_cap = n;
+        }
+        cudaStream_t s = c->slot[0].stream;
+        const size_t bytes = (size_t)n * sizeof(float);
+        cudaMemcpyAsync(c->big_x, hx, bytes, cudaMemcpyHostToDevice, s);
+        if (bwd) cudaMemcpyAsync(c->big_g, hg, bytes, cudaMemcpyHostToDevice, s);
+        rc = bwd ? qd_uniform_fwd_bwd(c->big_x, c->big_g, c->big_q, c->big_gout, n, bucket, levels, mode, c->big_ws,
+                                      c->big_ws_bytes, s)
+                 : qd_uniform_fwd(c->big_x, c->big_q, nullptr, nullptr, nullptr, nullptr, nullptr, n, bucket, levels,
+                                  nullptr, 0.f, 0, 0, 0, c->big_ws, c->big_ws_bytes, s);
+        if (rc) return rc;
+        cudaMemcpyAsync(hq, c->big_q, bytes, cudaMemcpyDeviceToHost, s);
+        if (bwd) cudaMemcpyAsync(hgout, c->big_gout, bytes, cudaMemcpyDeviceToHost, s);
+        return cudaStreamSynchronize(s) == cudaSuccess ? QD_OK : QD_ERR_CUDA;
+    }
+
+    // row-aligned chunks; the kernel sees each chunk as an independent tensor with the
+    // same bucket size, which is exact because rows never straddle a chunk boundary and
+    // only the last chunk holds the (short) tail row.
+    const int64_t rows_per_chunk = kChunkElems / row_len;
+    const int64_t chunk = rows_per_chunk * row_len;
+    int k = 0;
+    for (int64_t off = 0; off < n; off += chunk, ++k) {
+        Slot& s = c->slot[k % kSlots];
+        const int64_t len = (n - off < chunk) ? (n - off) : chunk;
+        const size_t bytes = (size_t)len * sizeof(float);
+        // a chunk shorter than the bucket must still be bucketed like the tail of the
+        // full tensor: with rows >= 2 overall the tail row is "padded", never a short
+        // single row -- both cases give the same min/max, so passing bucket is exact.
+        cudaMemcpyAsync(s.x, hx + off, bytes, cudaMemcpyHostToDevice, s.stream);
+        if (bwd) cudaMemcpyAsync(s.g, hg + off, bytes, cudaMemcpyHostToDevice, s.stream);
+        rc = bwd ? qd_uniform_fwd_bwd(s.x, s.g, s.q, s.gout, len, bucket, levels, mode, s.ws, s.ws_bytes, s.stream)
+                 : qd_uniform_fwd(s.x, s.q, nullptr, nullptr, nullptr, nullptr, nullptr, len, bucket, levels, nullptr,
+                                  0.f, 0, 0, 0, s.ws, s.ws_bytes, s.stream);
+        if (rc) return rc;
+        cudaMemcpyAsync(hq + off, s.q, bytes, cudaMemcpyDeviceToHost, s.stream);
+        if (bwd) cudaMemcpyAsync(hgout + off, s.gout, bytes, cudaMemcpyDeviceToHost, s.stream);
+    }
+    for (int i = 0; i < kSlots; ++i)
+        if (cudaStreamSynchronize(c->slot[i].stream) != cudaSuccess) return QD_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? QD_OK : QD_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" int qd_uniform_fwd_host(const float* x_host, float* q_host, int64_t n, int64_t bucket, int levels, int device) {
+    return run_host(x_host, nullptr, q_host, nullptr, n, bucket, levels, 0, device);
+}
+
+extern "C" int qd_uniform_fwd_bwd_host(const float* x_host, const float* g_host, float* q_host, float* gout_host,
+                                       int64_t n, int64_t bucket, int levels, int mode, int device) {
+    if (g_host == nullptr) return QD_ERR_INVALID_ARG;
+    return run_host(x_host, g_host, q_host, gout_host, n, bucket, levels, mode, device);
+}

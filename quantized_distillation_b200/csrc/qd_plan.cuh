@@ -1,0 +1,70 @@
+// qd_plan.cuh -- one launch over every parameter tensor of a model (SURVEY.md
+// section 8 f1).  The training loop of the reference quantizes the model one
+// tensor at a time (cnn_models/conv_forward_model.py:236-247: 22-60 tensors,
+// ~12 stock launches each); most of those tensors are 10-500 elements and are
+// pure launch latency.  A plan flattens all rows of all tensors into one row
+// space; a warp maps its global row to (tensor, local row) with a binary search
+// over the per-tensor row prefix held in shared memory and then runs exactly
+// the single-tensor warp path on it.
+#pragma once
+#include "qd_warp_path.cuh"
+
+namespace qd {
+
+struct PlanEntry {
+    const float* src;
+    float* dst;
+    int64_t n;
+    int64_t row_start;  // first global row of this tensor
+    int64_t rows;
+    int64_t row_len;
+    float S;            // levels - 1
+    int vec;            // 16-byte aligned rows
+};
+
+constexpr int kPlanSmemEntries = 256;
+
+template <int BWD, int R>
+__global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEntry* __restrict__ entries, int count,
+                                                                   int64_t total_rows, float* const* __restrict__ grads) {
+    __shared__ int64_t s_start[kPlanSmemEntries];
+    const bool in_smem = count <= kPlanSmemEntries;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) s_start[i] = entries[i].row_start;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    Centroids cen{nullptr, nullptr, 0};
+    for (int64_t grow = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); grow < total_rows; grow += stride) {
+        int lo = 0, hi = count - 1;  // largest t with row_start[t] <= grow
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            int64_t s = in_smem ? s_start[mid] : entries[mid].row_start;
+            if (s <= grow) lo = mid; else hi = mid - 1;
+        }
+        const PlanEntry en = entries[lo];
+        Params P;
+        P.x = en.src;
+        P.q = (BWD == BWD_OFF) ? en.dst : nullptr;
+        P.g = (BWD == BWD_OFF) ? nullptr : grads[lo];
+        P.gout = (BWD == BWD_OFF) ? nullptr : grads[lo];
+        P.xhat = nullptr; P.idx8 = nullptr; P.idx64 = nullptr;
+        P.alpha = nullptr; P.beta = nullptr; P.argmin = nullptr; P.argmax = nullptr;
+        P.mean = nullptr; P.max_element = 0.f; P.points = nullptr; P.num_points = 0; P.rule = 0;
+        P.geo.n = en.n; P.geo.row_len = en.row_len; P.geo.rows = en.rows;
+        P.S = en.S; P.stochastic = 0; P.seed = 0; P.offset = 0;
+        const int64_t row = grow - en.row_start;
+        bool vec = en.vec != 0;
+        if constexpr (BWD != BWD_OFF) vec = vec && ((reinterpret_cast<uintptr_t>(P.g) & 15) == 0);
+        if (vec) {
+            const bool full = (en.row_len == R * 128) && ((row + 1) * en.row_len <= en.n);
+            if (full) warp_process_row<OP_UNIFORM, BWD, R, true, true>(P, cen, row, lane);
+            else warp_process_row<OP_UNIFORM, BWD, R, true, false>(P, cen, row, lane);
+        } else {
+            warp_process_row<OP_UNIFORM, BWD, R, false, false>(P, cen, row, lane);
+        }
+    }
+}
+
+}  // namespace qd

@@ -1,0 +1,305 @@
+// qd_warp_path.cuh -- rows of at most 1024 elements: ONE WARP PER ROW, the row
+// lives in registers between the reduction and the element-wise pass, so every
+// byte crosses HBM exactly once (8 B/elt forward, 16 B/elt fused fwd+bwd).
+//
+// Layout: lane L of the warp owns elements r*128 + 4L .. 4L+3 of the row
+// (r = 0..R-1), i.e. each load/store instruction of the warp covers 512
+// contiguous bytes (4 full 128-byte lines).  Rows that are not 16-byte aligned
+// (bucket % 4 != 0 or an offset base pointer) use the scalar mapping
+// (r*4+j)*32 + L, still fully coalesced.  Row reductions are single
+// CREDUX.F32 instructions (redux.sync.{min,max}.NaN.f32, sm_100a).
+//
+// The grid is persistent: min(ceil(rows / warps_per_cta), SMs * resident CTAs)
+// CTAs, each warp walking rows with a grid stride, so consecutive warps stream
+// consecutive rows.
+#pragma once
+#include "qd_rowops.cuh"
+
+namespace qd {
+
+constexpr int kWarpCtaThreads = 256;
+constexpr int kWarpsPerCta = kWarpCtaThreads / 32;
+
+template <int R, bool VEC>
+__device__ __forceinline__ int elem_index(int r, int j, int lane) {
+    return VEC ? (r * 128 + lane * 4 + j) : ((r * 4 + j) * 32 + lane);
+}
+
+template <int R, bool VEC, bool FULL>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, int len, int lane, float (&v)[4 * R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (VEC && (FULL || r * 128 + lane * 4 + 4 <= len)) {
+            float4 t = ld_stream4(p + r * 128 + lane * 4);
+            v[4 * r + 0] = t.x; v[4 * r + 1] = t.y; v[4 * r + 2] = t.z; v[4 * r + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int e = elem_index<R, VEC>(r, j, lane);
+                v[4 * r + j] = (e < len) ? ld_stream1(p + e) : 0.f;
+            }
+        }
+    }
+}
+
+template <int R, bool VEC, bool FULL>
+__device__ __forceinline__ void store_row(float* __restrict__ p, int len, int lane, const float (&v)[4 * R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (VEC && (FULL || r * 128 + lane * 4 + 4 <= len)) {
+            st_stream4(p + r * 128 + lane * 4, make_float4(v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int e = elem_index<R, VEC>(r, j, lane);
+                if (e < len) st_stream1(p + e, v[4 * r + j]);
+            }
+        }
+    }
+}
+
+template <int R, bool VEC, bool FULL>
+__device__ __forceinline__ void store_row_u8(uint8_t* __restrict__ p, int len, int lane, const float (&lv)[4 * R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (VEC && (FULL || r * 128 + lane * 4 + 4 <= len) && ((reinterpret_cast<uintptr_t>(p) & 3) == 0)) {
+            uint32_t w = (uint32_t)(int)lv[4 * r] | ((uint32_t)(int)lv[4 * r + 1] << 8) |
+                         ((uint32_t)(int)lv[4 * r + 2] << 16) | ((uint32_t)(int)lv[4 * r + 3] << 24);
+            *reinterpret_cast<uint32_t*>(p + r * 128 + lane * 4) = w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int e = elem_index<R, VEC>(r, j, lane);
+                if (e < len) p[e] = (uint8_t)(int)lv[4 * r + j];
+            }
+        }
+    }
+}
+
+// first index (inside the row) whose value equals `target`; rows are < 2^31 long
+template <int R, bool VEC, bool FULL>
+__device__ __forceinline__ int first_equal(const float (&v)[4 * R], float target, int len, int lane) {
+    int best = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int e = elem_index<R, VEC>(r, j, lane);
+            if ((FULL || e < len) && v[4 * r + j] == target) best = min(best, e);
+        }
+    return warp_min_int(best);
+}
+
+// One row, one warp.  OP / BWD / WANT_* are compile-time so the hot forward
+// kernel carries no dead code.
+template <int OP, int BWD, int R, bool VEC, bool FULL>
+__device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen, int64_t row, int lane) {
+    constexpr int E = 4 * R;
+    const int64_t base = row * P.geo.row_len;
+    const int len = FULL ? R * 128 : (int)min(P.geo.row_len, P.geo.n - base);
+
+    float v[E];
+    load_row<R, VEC, FULL>(P.x + base, len, lane, v);
+
+    float gv[E];
+    if constexpr (BWD != BWD_OFF) load_row<R, VEC, FULL>(P.g + base, len, lane, gv);
+
+    RowState rs;
+    rs.mean = 0.f;
+    const bool pre = (P.mean != nullptr) || (P.max_element > 0.f);
+    if (pre) {
+        rs.mean = P.mean ? *P.mean : 0.f;
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i] = pre_op(v[i], rs.mean, P.max_element);
+    }
+
+    // ---- row reduction: beta = min, alpha = max - min ----------------------
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (FULL || elem_index<R, VEC>(r, j, lane) < len) {
+                mn = min_nan(mn, v[4 * r + j]);
+                mx = max_nan(mx, v[4 * r + j]);
+            }
+        }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    rs.beta = mn;
+    rs.alpha = make_alpha(mn, mx);
+
+    if (P.alpha != nullptr && lane == 0) {
+        P.alpha[row] = rs.alpha;
+        P.beta[row] = rs.beta;
+    }
+    if (P.argmin != nullptr) {  // first occurrence, like torch.min/max(dim) on CPU
+        int imin = first_equal<R, VEC, FULL>(v, mn, len, lane);
+        int imax = first_equal<R, VEC, FULL>(v, mx, len, lane);
+        if (lane == 0) {
+            P.argmin[row] = (imin == 0x7fffffff) ? 0 : imin;  // all-NaN rows: index 0
+            P.argmax[row] = (imax == 0x7fffffff) ? 0 : imax;
+        }
+    }
+    if constexpr (OP == OP_STATS) return;
+
+    if constexpr (OP == OP_SCALE) {
+        // x_hat in the padded layout: the tail row is filled with x_hat of the
+        // last element (help_functions.py:75-76, 83-86)
+        const int64_t pbase = row * P.geo.row_len;
+        float o[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) o[i] = to_unit(v[i], rs.beta, rs.alpha);
+        if (FULL) {
+            store_row<R, VEC, true>(P.xhat + pbase, len, lane, o);
+        } else {
+            const int plen = (int)P.geo.row_len;  // padded row length
+            if (len < plen) {
+                float last = P.x[P.geo.n - 1];
+                if (pre) last = pre_op(last, rs.mean, P.max_element);
+                last = to_unit(last, rs.beta, rs.alpha);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (elem_index<R, VEC>(r, j, lane) >= len) o[4 * r + j] = last;
+            }
+            store_row<R, VEC, false>(P.xhat + pbase, plen, lane, o);
+        }
+        return;
+    }
+
+    if constexpr (OP == OP_UNIFORM) {
+        float qv[E];
+        float lv[E];
+        if (P.stochastic) {
+            Philox rng(P.seed);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // one Philox block per 4 consecutive elements of the padded layout
+                int e0 = elem_index<R, VEC>(r, 0, lane);
+                if (VEC) {
+                    uint4 rnd = rng(P.offset + (uint64_t)((base + e0) >> 2));
+                    qv[4 * r + 0] = uniform_quantize_stochastic(v[4 * r + 0], rs, P.S, u01(rnd.x), lv[4 * r + 0]);
+                    qv[4 * r + 1] = uniform_quantize_stochastic(v[4 * r + 1], rs, P.S, u01(rnd.y), lv[4 * r + 1]);
+                    qv[4 * r + 2] = uniform_quantize_stochastic(v[4 * r + 2], rs, P.S, u01(rnd.z), lv[4 * r + 2]);
+                    qv[4 * r + 3] = uniform_quantize_stochastic(v[4 * r + 3], rs, P.S, u01(rnd.w), lv[4 * r + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int64_t ge = base + elem_index<R, VEC>(r, j, lane);
+                        uint4 rnd = rng(P.offset + (uint64_t)(ge >> 2));
+                        uint32_t w = (ge & 3) == 0 ? rnd.x : (ge & 3) == 1 ? rnd.y : (ge & 3) == 2 ? rnd.z : rnd.w;
+                        qv[4 * r + j] = uniform_quantize_stochastic(v[4 * r + j], rs, P.S, u01(w), lv[4 * r + j]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < E; ++i) qv[i] = uniform_quantize(v[i], rs, P.S, lv[i]);
+        }
+
+        if constexpr (BWD == BWD_MINMAX) {
+            // Second scaling: the reference re-scales q with the same ScalingFunction
+            // object, so alpha', beta', argmin', argmax' are those of q
+            // (quant_functions.py:350-363).  q is monotone in the level, so
+            // min q / max q are exact float reductions over qv.
+            float qmn = __int_as_float(0x7f800000), qmx = __int_as_float(0xff800000);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (FULL || elem_index<R, VEC>(r, j, lane) < len) {
+                        qmn = min_nan(qmn, qv[4 * r + j]);
+                        qmx = max_nan(qmx, qv[4 * r + j]);
+                    }
+            qmn = warp_min(qmn);
+            qmx = warp_max(qmx);
+            rs.beta2 = qmn;
+            rs.alpha2 = make_alpha(qmn, qmx);
+            int imin = first_equal<R, VEC, FULL>(qv, qmn, len, lane);
+            int imax = first_equal<R, VEC, FULL>(qv, qmx, len, lane);
+            // r_b = sum_j v_j: per-lane float32 partials, float64 across the warp
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (FULL || elem_index<R, VEC>(r, j, lane) < len)
+                        acc += (double)minmax_term(v[4 * r + j], qv[4 * r + j], gv[4 * r + j], rs);
+            const float rb = (float)warp_sum(acc);
+            if (imin != imax) {  // +r at argmax', -r at argmin' (the +1/-1 columns of grad_alpha, :380-393)
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int e = elem_index<R, VEC>(r, j, lane);
+                        if (e == imax) gv[4 * r + j] = __fadd_rn(gv[4 * r + j], rb);
+                        if (e == imin) gv[4 * r + j] = __fadd_rn(gv[4 * r + j], -rb);
+                    }
+            }
+        } else if constexpr (BWD == BWD_TRUNC) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) gv[i] = (fabsf(v[i]) > 1.0f) ? 0.f : gv[i];
+        }
+
+        if (P.q != nullptr) {
+            if (pre) {
+#pragma unroll
+                for (int i = 0; i < E; ++i) qv[i] = __fadd_rn(qv[i], rs.mean);  // quant_functions.py:148
+            }
+            store_row<R, VEC, FULL>(P.q + base, len, lane, qv);
+        }
+        if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, lv);
+        if constexpr (BWD != BWD_OFF) store_row<R, VEC, FULL>(P.gout + base, len, lane, gv);
+        return;
+    }
+
+    if constexpr (OP == OP_NONUNIFORM) {
+        float qv[E];
+        float lv[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            float xh = to_unit(v[i], rs.beta, rs.alpha);
+            int id = centroid_index(cen, xh, P.rule);
+            lv[i] = (float)id;
+            qv[i] = from_unit(cen.k[id], rs.alpha, rs.beta);
+            if (pre) qv[i] = __fadd_rn(qv[i], rs.mean);
+        }
+        if (P.q != nullptr) store_row<R, VEC, FULL>(P.q + base, len, lane, qv);
+        if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, lv);
+        if (P.idx64 != nullptr) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int e = elem_index<R, VEC>(r, j, lane);
+                    if (FULL || e < len) P.idx64[base + e] = (int64_t)lv[4 * r + j];
+                }
+        }
+        return;
+    }
+}
+
+template <int OP, int BWD, int R, bool VEC>
+__global__ void __launch_bounds__(kWarpCtaThreads) warp_rows_kernel(const __grid_constant__ Params P) {
+    __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
+    __shared__ float s_m[OP == OP_NONUNIFORM ? 256 : 1];
+    Centroids cen{s_k, s_m, P.num_points};
+    if constexpr (OP == OP_NONUNIFORM) {
+        centroid_setup(s_k, s_m, P.points, P.num_points);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    const bool row_is_full = VEC && (P.geo.row_len == R * 128);
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < P.geo.rows; row += stride) {
+        const bool full = row_is_full && ((row + 1) * P.geo.row_len <= P.geo.n);
+        if (full)
+            warp_process_row<OP, BWD, R, VEC, VEC>(P, cen, row, lane);  // FULL only exists for VEC
+        else
+            warp_process_row<OP, BWD, R, VEC, false>(P, cen, row, lane);
+    }
+}
+
+}  // namespace qd

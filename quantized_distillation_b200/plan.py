@@ -1,0 +1,93 @@
+"""Multi-tensor quantization plan: ONE kernel launch quantizes every parameter
+tensor of a model.
+
+The reference walks ``model.parameters()`` and calls ``uniformQuantization`` per
+tensor (cnn_models/conv_forward_model.py:236-247), keeps the full-precision
+weights alive through ``model.state_dict()`` and copies them back with
+``load_state_dict`` (:286, :302).  Here the full-precision master copy lives in
+one flat shadow buffer, the live parameters are quantized IN PLACE (so DDP's
+parameter references stay valid), and save / quantize / restore / gradient
+fix-up are each a single launch regardless of the number of tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+_STYLE = {"none": N.BWD_STE, None: N.BWD_STE, "truncated": N.BWD_TRUNCATED, "complicated": N.BWD_MINMAX}
+
+
+class QuantizationPlan:
+    def __init__(self, params, levels, bucket_size=None):
+        N.require_cuda()
+        self.params = [p.data if isinstance(p, torch.nn.Parameter) else p for p in params]
+        if not self.params:
+            raise ValueError("no tensors to quantize")
+        for p in self.params:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise ValueError("plan tensors must be contiguous float32 CUDA tensors")
+        self.device = self.params[0].device
+        self.bucket_size = bucket_size
+        count = len(self.params)
+        self.levels = [int(levels)] * count if isinstance(levels, int) else [int(v) for v in levels]
+        if len(self.levels) != count:
+            raise ValueError("one level count per tensor expected")
+        self._ptrs = (C.c_void_p * count)(*[p.data_ptr() for p in self.params])
+        self._n = (C.c_int64 * count)(*[p.numel() for p in self.params])
+        self._lv = (C.c_int32 * count)(*self.levels)
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().qd_plan_create(C.byref(self._handle), count, self._ptrs, self._ptrs, self._n, self._lv,
+                                           0 if bucket_size is None else int(bucket_size)))
+        total = sum(p.numel() for p in self.params)
+        self._master_flat = torch.empty(total, dtype=torch.float32, device=self.device)
+        self._master, off = [], 0
+        for p in self.params:
+            self._master.append(self._master_flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        self.numel = total
+
+    # -- full-precision master copy ------------------------------------------------
+    def save_master(self):
+        """master <- params (replaces ``model_state_dict = model.state_dict()``, :286)."""
+        torch._foreach_copy_(self._master, self.params)
+        return self._master
+
+    def restore_master(self):
+        """params <- master (replaces ``model.load_state_dict(model_state_dict)``, :302)."""
+        torch._foreach_copy_(self.params, self._master)
+
+    # -- quantization -----------------------------------------------------------------
+    def quantize_(self):
+        """params <- uniformQuantization(params), every tensor, one launch (:236-247)."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib().qd_plan_uniform_fwd(self._handle, N.stream_ptr(self.device)))
+
+    def backward_(self, grads, style):
+        """grads <- gradient fix-up of the chosen backprop_quantization_style, in place,
+        evaluated at the CURRENT (full-precision, i.e. restored) params (:249-266)."""
+        mode = _STYLE[style]
+        if mode == N.BWD_STE:
+            return
+        if len(grads) != len(self.params):
+            raise ValueError("one gradient per tensor expected")
+        for g, p in zip(grads, self.params):
+            if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == p.numel()):
+                raise ValueError("gradients must be contiguous float32 CUDA tensors matching the params")
+        gp = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(self.device):
+            N.check(N.lib().qd_plan_uniform_bwd(self._handle, gp, mode, N.stream_ptr(self.device)))
+
+    def close(self):
+        if self._handle:
+            N.lib().qd_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

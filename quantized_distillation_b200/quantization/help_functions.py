@@ -1,0 +1,174 @@
+"""B200 counterpart of the reference's ``quantization/help_functions.py``:
+bucketing view, centroid initialisation, bit allocation and Huffman statistics.
+Only what the quantized-distillation / differentiable-quantization loops and the
+size accounting call is provided (the hyperspherical helpers, :8-65, are unused
+by the reference itself)."""
+from __future__ import annotations
+
+import heapq
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+__all__ = ("create_bucket_tensor", "assign_bits_automatically", "initialize_quantization_points", "huffman_encode",
+           "get_huffman_encoding_mean_bit_length", "index_histogram")
+
+
+def create_bucket_tensor(tensor, bucket_size, fill_values="last"):
+    """Row view of a tensor: ``(ceil(n/b), b)`` with the tail padded with the
+    last element (or NaN), ``(1, n)`` when n < b (reference: help_functions.py:67-94).
+    The kernels never materialise this view -- they do the index arithmetic --
+    so this is only for callers that want the padded tensor itself."""
+    if bucket_size is None:
+        return tensor
+    tensor = tensor.view(-1)
+    n = tensor.numel()
+    multiple, rest = divmod(n, bucket_size)
+    if multiple != 0 and rest != 0:
+        fill = float("nan") if fill_values == "nan" else tensor[-1]
+        pad = torch.ones(bucket_size - rest, dtype=tensor.dtype, device=tensor.device) * fill
+        tensor = torch.cat([tensor, pad])
+    return tensor.view(1, n) if multiple == 0 else tensor.view(-1, bucket_size)
+
+
+def assign_bits_automatically(gradient_norms, inital_bits_to_assign, input_is_point=False):
+    """Redistribute a bit (or point) budget across tensors in proportion to
+    their gradient norms (reference: help_functions.py:97-138)."""
+    norms = [float(g) for g in gradient_norms]
+    if isinstance(inital_bits_to_assign, int):
+        inital_bits_to_assign = [inital_bits_to_assign] * len(norms)
+    if len(inital_bits_to_assign) != len(norms):
+        raise ValueError("There should be as many gradients as there are initial points.")
+    budget = sum(inital_bits_to_assign)
+    floor_alloc = [x // 2 for x in inital_bits_to_assign] if input_is_point else [x - 1 for x in inital_bits_to_assign]
+    spare = budget - sum(floor_alloc)
+    total_norm = sum(norms)
+    alloc = [base + round(g / total_norm * spare) for g, base in zip(norms, floor_alloc)]
+    excess = sum(alloc) - budget
+    if excess > 0:
+        alloc[alloc.index(max(alloc))] -= excess
+    elif excess < 0:
+        alloc[alloc.index(min(alloc))] += -excess
+    return alloc
+
+
+def percentile_plan(n: int, num_points: int, dtype=np.float32):
+    """Which order statistics ``np.percentile(v, linspace(0,100,K))`` reads and
+    with which weights, for ``len(v) == n`` and ``method='linear'``.  Uses
+    numpy's own index arithmetic (numpy/lib/_function_base_impl.py:
+    _QuantileMethods['linear'], _get_indexes, _get_gamma) so the selection is the one
+    numpy makes.  Returns (prev_idx, next_idx, gamma)."""
+    from numpy.lib import _function_base_impl as F
+    q = np.true_divide(np.linspace(0, 100, num=num_points), dtype(100))
+    virt = np.asanyarray(F._QuantileMethods["linear"]["get_virtual_index"](n, q))
+    prev, nxt = F._get_indexes(np.empty(1, dtype=dtype), virt, n)
+    gamma = np.asanyarray(virt - prev, dtype=virt.dtype)
+    return prev, nxt, gamma
+
+
+def percentile_combine(prev_vals: np.ndarray, next_vals: np.ndarray, gamma: np.ndarray) -> np.ndarray:
+    """numpy's linear interpolation of the two neighbours (_lerp)."""
+    from numpy.lib import _function_base_impl as F
+    return np.asarray(F._lerp(prev_vals, next_vals, gamma))
+
+
+def initialize_quantization_points(tensor, scaling_function, num_points):
+    """Percentile initialisation of the centroids on the scaled tensor
+    (reference: help_functions.py:140-154).  The scaling and a sort run on the
+    GPU; only the 2K order statistics numpy's percentile would read are brought
+    to the host and combined with numpy's own interpolation, so the result is
+    bit-identical to ``np.percentile`` over the whole array."""
+    scaled = scaling_function.scale_down(tensor).view(-1)[0:scaling_function.original_tensor_length]
+    n = scaled.numel()
+    if not scaled.is_cuda:
+        N.require_cuda()
+        scaled = scaled.cuda()
+    ordered = torch.sort(scaled)[0]
+    prev, nxt, gamma = percentile_plan(n, num_points)
+    sel = torch.from_numpy(np.concatenate([prev % n, nxt % n]).astype(np.int64)).to(ordered.device)
+    picks = ordered[sel].cpu().numpy()
+    initial_points = percentile_combine(picks[:num_points], picks[num_points:], gamma)
+    initial_points = torch.from_numpy(np.asarray(initial_points)).type_as(tensor)
+    return initial_points.to(tensor.device)
+
+
+def huffman_encode(symb2freq):
+    """Huffman code of a {symbol: weight} dict as a list of [symbol, code]
+    (reference: help_functions.py:157-172)."""
+    heap = [[wt, [sym, ""]] for sym, wt in symb2freq.items()]
+    heapq.heapify(heap)
+    while len(heap) > 1:
+        lo, hi = heapq.heappop(heap), heapq.heappop(heap)
+        for pair in lo[1:]:
+            pair[1] = "0" + pair[1]
+        for pair in hi[1:]:
+            pair[1] = "1" + pair[1]
+        heapq.heappush(heap, [lo[0] + hi[0]] + lo[1:] + hi[1:])
+    return sorted(heapq.heappop(heap)[1:], key=lambda p: (len(p[-1]), p))
+
+
+def index_histogram(idx_u8: torch.Tensor, num_bins: int, counts: torch.Tensor = None) -> torch.Tensor:
+    """counts[b] += #{idx == b} on the GPU (qd_index_histogram)."""
+    N.require_cuda()
+    idx_u8 = idx_u8.contiguous().view(-1)
+    if counts is None:
+        counts = torch.zeros(num_bins, dtype=torch.int64, device=idx_u8.device)
+    N.check(N.lib().qd_index_histogram(N.ptr(idx_u8), idx_u8.numel(), num_bins, N.ptr(counts), N.stream_ptr(idx_u8.device)))
+    return counts
+
+
+def get_huffman_encoding_mean_bit_length(model_param_iter, quantization_functions, type_quantization="uniform", s=None):
+    """Mean Huffman code length over the quantization indices of a whole model
+    (reference: help_functions.py:175-232).
+
+    ``quantization_functions`` are callables with the reference's contracts:
+    uniform -> ``(q, ScalingFunction)``, nonUniform -> ``(q, indices, sf)``.  For
+    the uniform case the reference recovers the integer level from the
+    quantized tensor with ``np.digitize`` on the re-scaled values (:213-218);
+    here the same re-scaling runs on the GPU and the level is
+    ``floor(x_hat*(s-1) + 1e-5*(s-1))``-equivalent digitisation done on device,
+    followed by a device histogram -- no per-tensor numpy round trip."""
+    type_quantization = type_quantization.lower()
+    if type_quantization not in ("uniform", "nonuniform"):
+        raise ValueError("type_quantization not recognized")
+    if s is None and type_quantization == "uniform":
+        raise ValueError("If type of quantization is uniform, you must provide s")
+    if not isinstance(quantization_functions, list):
+        quantization_functions = [quantization_functions]
+    single = len(quantization_functions) == 1
+    total_length = 0
+    counts = None
+    tol = 1e-5
+    for idx, param in enumerate(model_param_iter):
+        param = param.data if hasattr(param, "data") else param
+        param = param.clone()
+        total_length += param.numel()
+        quant_fun = quantization_functions[0] if single else quantization_functions[idx]
+        if type_quantization == "uniform":
+            q_tensor, scal = quant_fun(param)
+            scaled = scal.scale_down(q_tensor).view(-1)[0:scal.original_tensor_length]
+            edges = torch.tensor([x / (s - 1) - tol for x in range(s)], dtype=torch.float64, device=scaled.device)
+            # np.digitize(v, edges) - 1 == (number of edges <= v) - 1, compared in float64 like numpy does
+            bins = (torch.searchsorted(edges, scaled.to(torch.float64), right=True) - 1).clamp_(min=0)
+            nbins = s
+        else:
+            _, bins, _ = quant_fun(param)
+            bins = bins.view(-1)
+            nbins = 256
+        bins_u8 = bins.to(torch.uint8)
+        if not bins_u8.is_cuda:
+            N.require_cuda()
+            bins_u8 = bins_u8.cuda()
+        if counts is None:
+            counts = torch.zeros(256, dtype=torch.int64, device=bins_u8.device)
+        index_histogram(bins_u8, max(nbins, 1), counts)
+    counts = counts.cpu().numpy()
+    assert total_length == int(counts.sum())                                              # :227
+    frequency = defaultdict(int)
+    for val in np.nonzero(counts)[0]:
+        frequency[int(val)] = counts[val] / total_length
+    code = huffman_encode(frequency)
+    return sum(frequency[sym] * len(bits) for sym, bits in code)

@@ -1,0 +1,152 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the
+header declares, host-side logic matches the reference, argument validation raises
+the reference's exception types, and the product never silently falls back to CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "qd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from quantized_distillation_b200 import _native as N
+    assert os.path.exists(N.LIB_PATH), "build the extension first: python -c 'import __graft_entry__ as g; g.build()'"
+    handle = ctypes.CDLL(N.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in include/qd_b200.h but not exported"
+    assert set(N.SIGNATURES) == set(syms), set(N.SIGNATURES) ^ set(syms)
+    assert N.lib().qd_version() >= 100
+
+
+def test_geometry_matches_oracle_without_gpu():
+    from oracle import quant_oracle as O
+    from quantized_distillation_b200 import _native as N
+    for n in (1, 10, 255, 256, 257, 1000, 4099, 1 << 26):
+        for b in (None, 1, 7, 256, 1024, 100000):
+            assert N.geometry(n, 0 if b is None else b) == O.bucket_geometry(n, b)
+    with pytest.raises(ValueError):
+        N.geometry(0, 256)
+    assert N.lib().qd_workspace_bytes(1 << 34, 0) >= N.lib().qd_workspace_bytes(1 << 20, 256) > 0
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every op raises instead of computing on the host."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import quantized_distillation_b200.quantization as Q
+    x = torch.randn(1000)
+    with pytest.raises(RuntimeError):
+        Q.uniformQuantization(x, 16, bucket_size=256)
+    with pytest.raises(RuntimeError):
+        Q.nonUniformQuantization(x, [0.0, 0.5, 1.0], bucket_size=256)
+    with pytest.raises(RuntimeError):
+        Q.ScalingFunction("linear", False, False, 256).scale_down(x)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "quantized_distillation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in text, f"{f} reads the reference at run time"
+
+
+def test_argument_validation_matches_reference_exceptions():
+    import quantized_distillation_b200.quantization as Q
+    with pytest.raises(ValueError):
+        Q.ScalingFunction("cubic", False, False, None)
+    with pytest.raises(ValueError):
+        Q.ScalingFunction("linear", False, False, 0)
+    with pytest.raises(ValueError):
+        Q.ScalingFunction("linear", False, False, 2.5)
+    with pytest.raises(ValueError):
+        Q.ScalingFunction("linear", True, False, None)
+    with pytest.raises(NotImplementedError):
+        Q.ScalingFunction("absmax", False, False, None)
+    with pytest.raises(ValueError):
+        Q.nonUniformQuantization(torch.randn(4), [0.0, 1.0], scaling_function=object())
+    with pytest.raises(ValueError):
+        Q.nonUniformQuantization_variable(pre_process_tensors=True, tensor=None)
+    with pytest.raises(TypeError):
+        Q.uniformQuantization(torch.randn(4).double(), 16)
+    f = Q.uniformQuantization_variable(16, bucket_size=256)
+    with pytest.raises(ValueError):
+        f.backward(torch.randn(4))
+    assert Q.__all__ == ("uniformQuantization", "ScalingFunction", "nonUniformQuantization",
+                         "uniformQuantization_variable", "nonUniformQuantization_variable")
+
+
+def test_install_as_quantization_aliases_the_reference_name():
+    import sys
+    import quantized_distillation_b200 as pkg
+    saved = {k: sys.modules.get(k) for k in ("quantization", "quantization.quant_functions", "quantization.help_functions")}
+    try:
+        pkg.install_as_quantization()
+        import quantization
+        import quantization.help_functions as qhf
+        assert quantization.uniformQuantization is pkg.quantization.uniformQuantization
+        assert qhf.create_bucket_tensor is pkg.quantization.help_functions.create_bucket_tensor
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_create_bucket_tensor_semantics():
+    from oracle import quant_oracle as O
+    from quantized_distillation_b200.quantization.help_functions import create_bucket_tensor
+    for n in (1, 5, 256, 257, 1000):
+        for b in (None, 2, 256):
+            t = torch.arange(n, dtype=torch.float32)
+            got = create_bucket_tensor(t, b)
+            if b is None:
+                assert got is t
+            else:
+                assert np.array_equal(got.numpy(), O.bucketed(t.numpy(), b))
+    nanfill = create_bucket_tensor(torch.arange(5.0), 2, fill_values="nan")
+    assert torch.isnan(nanfill[-1, -1]) and nanfill.shape == (3, 2)
+
+
+def test_assign_bits_and_huffman_host_logic(golden):
+    from oracle import quant_oracle as O
+    from quantized_distillation_b200.quantization import help_functions as H
+    # assign_bits_automatically: budget is preserved, more gradient -> not fewer points
+    alloc = H.assign_bits_automatically([1.0, 2.0, 4.0, 1.0], 4, input_is_point=True)
+    assert sum(alloc) == 16 and alloc[2] == max(alloc)
+    alloc = H.assign_bits_automatically([1.0, 1.0], [4, 8])
+    assert sum(alloc) == 12
+    with pytest.raises(ValueError):
+        H.assign_bits_automatically([1.0], [4, 4])
+    code = dict((sym, bits) for sym, bits in H.huffman_encode({0: 0.5, 1: 0.25, 2: 0.125, 3: 0.125}))
+    assert [len(code[k]) for k in range(4)] == [1, 2, 3, 3]
+    counts = [50, 25, 13, 12]
+    freq = {i: c / 100 for i, c in enumerate(counts)}
+    mean = sum(freq[s] * len(b) for s, b in H.huffman_encode(freq))
+    assert abs(mean - O.huffman_mean_bit_length(counts)) < 1e-12
+
+
+def test_percentile_plan_is_numpy_percentile():
+    from quantized_distillation_b200.quantization import help_functions as H
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 10, 255, 1000, 4099):
+        for K in (2, 3, 4, 16, 40):
+            v = rng.random(n).astype(np.float32)
+            o = np.sort(v)
+            p, nx, g = H.percentile_plan(n, K)
+            assert np.array_equal(H.percentile_combine(o[p], o[nx], g), np.percentile(v, np.linspace(0, 100, num=K)))

@@ -1,0 +1,430 @@
+"""GPU parity: the CUDA path (through the C ABI / the reference-shaped Python
+surface) against (1) the golden vectors produced by the reference itself and
+(2) the oracle on seeded inputs.  Bit-exact for q / idx / alpha / beta /
+argmin / argmax; stated tolerance only for float32 sums whose order differs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import quant_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Q():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import quantized_distillation_b200.quantization as Q
+    return Q
+
+
+def bits(a):
+    a = np.ascontiguousarray(np.asarray(a))
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def assert_same(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not np.array_equal(bits(a), bits(b)):
+        # -0.0 vs +0.0 can never come out of the chain, so a plain bit compare is the bar
+        bad = np.nonzero(bits(a).reshape(-1) != bits(b).reshape(-1))[0]
+        raise AssertionError(f"{what}: {bad.size} mismatches, first at {bad[:5]}: {a.reshape(-1)[bad[:5]]} vs {b.reshape(-1)[bad[:5]]}")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ----------------------------------------------------------------------- golden vectors
+def test_uniform_forward_golden(Q, golden):
+    data, cases = golden
+    for c in cases["uniform"]:
+        k = c["key"]
+        q, sf = Q.uniformQuantization(dev(data[k + "_x"]), c["s"], bucket_size=c["bucket"])
+        assert_same(q.cpu().numpy(), data[k + "_q"], f"{k} q {c}")
+        assert_same(sf.alpha.reshape(-1).cpu().numpy(), data[k + "_alpha"], f"{k} alpha")
+        assert_same(sf.beta.reshape(-1).cpu().numpy(), data[k + "_beta"], f"{k} beta")
+        assert_same(sf.idx_min_rows.reshape(-1).cpu().numpy(), data[k + "_argmin"], f"{k} argmin {c}")
+        assert_same(sf.idx_max_rows.reshape(-1).cpu().numpy(), data[k + "_argmax"], f"{k} argmax")
+
+
+def test_scale_down_inverse_golden(Q, golden):
+    data, cases = golden
+    for c in cases["uniform"]:
+        k = c["key"]
+        sf = Q.ScalingFunction("linear", False, False, c["bucket"], False)
+        xh = sf.scale_down(dev(data[k + "_x"]))
+        assert_same(xh.reshape(-1).cpu().numpy(), data[k + "_xhat"], f"{k} xhat {c}")
+        y = dev(data[k + "_inv_in"]).view(xh.size())
+        assert_same(sf.inv_scale_down(y).reshape(-1).cpu().numpy(), data[k + "_inv_out"], f"{k} inv")
+
+
+def test_nonuniform_golden(Q, golden):
+    data, cases = golden
+    for c in cases["nonuniform"]:
+        k = c["key"]
+        x = dev(data[k + "_x"])
+        pts = dev(data[k + "_points"])
+        q, idx, sf = Q.nonUniformQuantization(x, pts, bucket_size=c["bucket"])
+        assert idx.dtype == torch.int64
+        assert_same(idx.cpu().numpy(), data[k + "_idx_nearest"], f"{k} idx nearest {c}")
+        assert_same(q.cpu().numpy(), data[k + "_q_nearest"], f"{k} q nearest")
+        assert_same(sf.alpha.reshape(-1).cpu().numpy(), data[k + "_alpha"], f"{k} alpha")
+        f = Q.nonUniformQuantization_variable(bucket_size=c["bucket"], pre_process_tensors=True, tensor=x)
+        q1 = f.forward(None, pts)
+        assert_same(q1.cpu().numpy(), data[k + "_q_midpoint"], f"{k} q midpoint")
+        assert_same(f.savedForBackward["indices"].cpu().numpy().astype(np.int64), data[k + "_idx_midpoint"], f"{k} idx midpoint")
+        q2 = f.forward(None, dev(data[k + "_points2"]))
+        assert_same(q2.cpu().numpy(), data[k + "_q_midpoint2"], f"{k} q midpoint2")
+        g = dev(data[k + "_g"])
+        gin, gp = f.backward(g)
+        assert gin is g
+        ref = data[k + "_gpoints2"].astype(np.float64)
+        scale = np.abs(data[k + "_g"]).astype(np.float64).sum() * float(data[k + "_alpha"].max())
+        assert np.abs(gp.cpu().numpy() - ref).max() <= 1e-6 * scale + 1e-12, (k, gp, ref)
+        # the hand-driven pre-processed path of the reference docstring (:218-227)
+        sfp = Q.ScalingFunction("linear", False, False, c["bucket"], False)
+        sso = Q.SearchSorted(sfp.scale_down(x).view(-1))
+        q3, idx3, _ = Q.nonUniformQuantization(None, pts, bucket_size=c["bucket"], pre_processed_values=True,
+                                               search_sorted_obj=sso, scaling_function=sfp, tensors_info=(x.type(), True))
+        assert_same(q3.cpu().numpy(), data[k + "_q_midpoint"], f"{k} q preprocessed")
+        assert_same(idx3.cpu().numpy(), data[k + "_idx_midpoint"], f"{k} idx preprocessed")
+
+
+def test_minmax_backward_golden(Q, golden):
+    data, cases = golden
+    for c in cases["minmax_bwd"]:
+        k = c["key"]
+        f = Q.uniformQuantization_variable(c["s"], bucket_size=c["bucket"])
+        f.forward(dev(data[k + "_x"]))
+        gout = f.backward(dev(data[k + "_g"])).cpu().numpy()
+        ref = data[k + "_gout"]
+        assert np.array_equal(np.nonzero(gout != data[k + "_g"])[0], np.nonzero(ref != data[k + "_g"])[0]), k
+        scale = np.abs(data[k + "_g"]).sum() / c["s"]
+        assert np.abs(gout.astype(np.float64) - ref).max() <= 1e-6 * scale + 1e-7, k
+
+
+def test_points_initialisation_golden(Q, golden):
+    data, cases = golden
+    for c in cases["init_points"]:
+        k = c["key"]
+        sf = Q.ScalingFunction("linear", False, False, c["bucket"], False)
+        pts = Q.help_functions.initialize_quantization_points(dev(data[k + "_x"]), sf, c["s"])
+        assert_same(pts.cpu().numpy(), data[k + "_points"], k)
+
+
+def test_huffman_golden(Q, golden):
+    data, cases = golden
+    for c in cases["huffman"]:
+        k = c["key"]
+        params = [dev(data[f"{k}_x{j}"]) for j in range(c["n"])]
+        fun = lambda t, s=c["s"], b=c["bucket"]: Q.uniformQuantization(t, s, bucket_size=b)  # noqa: E731
+        mbl = Q.help_functions.get_huffman_encoding_mean_bit_length(iter(params), fun, "uniform", s=c["s"])
+        assert abs(mbl - float(data[k + "_mean_bits"][0])) < 1e-9
+
+
+# ----------------------------------------------------------------------- oracle sweeps
+SIZES = [1, 3, 4, 5, 31, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 4096, 5000, 65536 + 17, 200003]
+BUCKETS = [None, 256, 512, 1024, 100, 7, 2048, 3000, 8192, 49152]
+
+
+@pytest.mark.parametrize("bucket", BUCKETS)
+def test_uniform_all_paths_vs_oracle(Q, bucket):
+    """Every execution path: warp (vec / scalar, R=2,4,8), block (TMA-staged), grid."""
+    rng = np.random.default_rng(7)
+    for n in SIZES + [300001]:
+        for s in (4, 16, 256):
+            x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+            if n > 10:
+                x[rng.integers(0, n, 3)] = x[0]          # duplicate extremes: first-occurrence ties
+            q, idx, st = O.uniform_fwd(x, s, bucket)
+            qd, sf = Q.uniformQuantization(dev(x), s, bucket_size=bucket)
+            assert_same(qd.cpu().numpy(), q, f"n={n} b={bucket} s={s}")
+            assert_same(sf.alpha.reshape(-1).cpu().numpy(), st["alpha"], "alpha")
+            assert_same(sf.beta.reshape(-1).cpu().numpy(), st["beta"], "beta")
+            assert_same(sf.idx_min_rows.reshape(-1).cpu().numpy(), st["argmin"], f"argmin n={n} b={bucket}")
+            assert_same(sf.idx_max_rows.reshape(-1).cpu().numpy(), st["argmax"], "argmax")
+
+
+def test_uniform_large_bucket_none_grid_path(Q):
+    rng = np.random.default_rng(11)
+    n = 3_000_017
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    q, idx, st = O.uniform_fwd(x, 16, None)
+    qd, sf = Q.uniformQuantization(dev(x), 16, bucket_size=None)
+    assert_same(qd.cpu().numpy(), q, "grid path q")
+    assert_same(sf.idx_min_rows.cpu().numpy(), st["argmin"], "grid argmin")
+    assert_same(sf.idx_max_rows.cpu().numpy(), st["argmax"], "grid argmax")
+
+
+def test_unaligned_views_and_in_place(Q):
+    rng = np.random.default_rng(3)
+    base = dev((rng.standard_normal(5000 + 3) * 0.1).astype(np.float32))
+    for off in (1, 2, 3):
+        v = base[off:off + 4097]                          # 4-byte aligned only
+        ref, _, _ = O.uniform_fwd(v.cpu().numpy(), 16, 256)
+        q, _ = Q.uniformQuantization(v, 16, bucket_size=256)
+        assert_same(q.cpu().numpy(), ref, f"offset {off}")
+    t = base[:4096].clone()
+    ref, _, _ = O.uniform_fwd(t.cpu().numpy(), 4, 256)
+    out, _ = Q.uniformQuantization(t, 4, bucket_size=256, modify_in_place=True)
+    assert out.data_ptr() == t.data_ptr()
+    assert_same(t.cpu().numpy(), ref, "in place")
+    # shape is preserved
+    w = dev(rng.standard_normal((7, 5, 3, 3)).astype(np.float32))
+    q, sf = Q.uniformQuantization(w, 16, bucket_size=256)
+    assert q.shape == w.shape and sf.alpha.shape == (2, 1) and sf.idx_min_rows.dtype == torch.int64
+
+
+def test_edge_inputs(Q):
+    # constant bucket (alpha -> 1), exact .5 ties (round half even), denormals, huge range
+    for x in (np.full(300, 0.125, np.float32),
+              np.array([0.0, 1.0] + [(2 * k + 1) / 30.0 for k in range(15)], np.float32),
+              np.array([0.0, 1e-40, 3e-39, 1e-38], np.float32),
+              np.array([-3e38, 3e38, 1.0, 0.0], np.float32),
+              np.array([1.0, 1.0 + 1e-7, 1.0 + 2e-7], np.float32)):
+        for s in (4, 16):
+            for b in (256, None, 2):
+                with np.errstate(all="ignore"):
+                    q, _, st = O.uniform_fwd(x, s, b)
+                qd, sf = Q.uniformQuantization(dev(x), s, bucket_size=b)
+                assert_same(qd.cpu().numpy(), q, f"edge {x[:4]} s={s} b={b}")
+    # NaN propagates through the whole bucket like torch.min/max do
+    x = np.arange(600, dtype=np.float32)
+    x[300] = np.nan
+    qd, _ = Q.uniformQuantization(dev(x), 16, bucket_size=256)
+    out = qd.cpu().numpy()
+    assert np.isnan(out[256:512]).all() and not np.isnan(out[:256]).any() and not np.isnan(out[512:]).any()
+
+
+@pytest.mark.parametrize("bucket", [256, 512, 1024, 100, 2048, 8192])
+def test_minmax_backward_vs_oracle(Q, bucket):
+    rng = np.random.default_rng(5)
+    for n in (1, 100, 256, 257, 1000, 4099, 20000):
+        for s in (4, 16, 256):
+            x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+            g = rng.standard_normal(n).astype(np.float32)
+            ref, info = O.uniform_bwd_minmax(x, g, s, bucket)
+            f = Q.uniformQuantization_variable(s, bucket_size=bucket)
+            f.forward(dev(x))
+            out = f.backward(dev(g)).cpu().numpy()
+            changed = np.nonzero(out != g)[0]
+            assert set(changed) <= set(info["argmax"]) | set(info["argmin"]), (n, s, bucket)
+            tol = 1e-6 * np.abs(g).sum() / max(1, n // bucket + 1) + 1e-6
+            assert np.abs(out.astype(np.float64) - ref).max() <= tol, (n, s, bucket, np.abs(out - ref).max())
+
+
+def test_fused_fwd_bwd_capi(Q):
+    """qd_uniform_fwd_bwd through ctypes: q identical to the forward op, gout identical to the backward op."""
+    from quantized_distillation_b200 import _native as N
+    rng = np.random.default_rng(9)
+    for n, b in ((4096, 256), (100000, 256), (5000, 512), (70001, 1024), (30000, 4096)):
+        x = dev((rng.standard_normal(n) * 2).astype(np.float32))
+        g = dev(rng.standard_normal(n).astype(np.float32))
+        ws = N.workspace(n, b, x.device)
+        for mode in (N.BWD_STE, N.BWD_TRUNCATED, N.BWD_MINMAX):
+            q, go = torch.empty_like(x), torch.empty_like(g)
+            N.check(N.lib().qd_uniform_fwd_bwd(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, b, 16, mode, N.ptr(ws), ws.numel(),
+                                               N.stream_ptr()))
+            qref, _, _ = O.uniform_fwd(x.cpu().numpy(), 16, b)
+            assert_same(q.cpu().numpy(), qref, f"fused q mode {mode}")
+            go2 = torch.empty_like(g)
+            N.check(N.lib().qd_uniform_bwd(N.ptr(x), N.ptr(g), N.ptr(go2), n, b, 16, mode, N.ptr(ws), ws.numel(), N.stream_ptr()))
+            assert_same(go.cpu().numpy(), go2.cpu().numpy(), f"fused gout mode {mode}")
+            if mode == N.BWD_STE:
+                assert_same(go.cpu().numpy(), g.cpu().numpy(), "ste")
+            if mode == N.BWD_TRUNCATED:
+                assert_same(go.cpu().numpy(), O.uniform_bwd_truncated(x.cpu().numpy(), g.cpu().numpy()), "trunc")
+
+
+@pytest.mark.parametrize("bucket", [None, 256, 1024, 100, 4096])
+def test_nonuniform_vs_oracle(Q, bucket):
+    rng = np.random.default_rng(13)
+    for n in (1, 10, 256, 257, 5000, 70001):
+        for K in (1, 2, 3, 4, 8, 9, 16, 40, 256):
+            x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+            pts = np.sort(rng.random(K)).astype(np.float32)
+            if K >= 4:
+                pts[1] = pts[2]                          # duplicate centroids
+            for rule, kw in (("nearest", {}), ("midpoint", {"pre": True})):
+                q, idx, st = O.nonuniform_fwd(x, pts, bucket, rule=rule)
+                if rule == "nearest":
+                    qd, idxd, sf = Q.nonUniformQuantization(dev(x), dev(pts), bucket_size=bucket)
+                    qd8, idx8, _ = Q.nonUniformQuantization(dev(x), dev(pts), bucket_size=bucket, index_dtype=torch.uint8)
+                    assert_same(idx8.cpu().numpy().astype(np.int64), idx, "u8 idx")
+                else:
+                    f = Q.nonUniformQuantization_variable(bucket_size=bucket, pre_process_tensors=True, tensor=dev(x))
+                    qd = f.forward(None, dev(pts))
+                    idxd = f.savedForBackward["indices"].to(torch.int64)
+                assert_same(idxd.cpu().numpy(), idx, f"{rule} idx n={n} K={K} b={bucket}")
+                assert_same(qd.cpu().numpy(), q, f"{rule} q n={n} K={K} b={bucket}")
+
+
+@pytest.mark.parametrize("bucket", [None, 256, 100])
+def test_points_gradient_vs_oracle(Q, bucket):
+    rng = np.random.default_rng(17)
+    for n in (1, 300, 4099, 300001):
+        for K in (2, 4, 8, 9, 16, 40):
+            x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+            g = rng.standard_normal(n).astype(np.float32)
+            pts = np.linspace(0, 1, K).astype(np.float32)
+            f = Q.nonUniformQuantization_variable(bucket_size=bucket, pre_process_tensors=True, tensor=dev(x))
+            f.forward(None, dev(pts))
+            _, gp = f.backward(dev(g))
+            _, idx, st = O.nonuniform_fwd(x, pts, bucket, rule="midpoint")
+            ref = O.nonuniform_bwd_points(g, idx, st["alpha"], K, bucket)
+            # float64 accumulation of float32 products: only the final cast to float32 differs from the exact sum
+            assert np.abs(gp.cpu().numpy().astype(np.float64) - ref).max() <= 1e-6 * np.abs(ref).max() + 1e-30, (n, K, bucket)
+            # deterministic: a second run is bit-identical
+            f.forward(None, dev(pts))
+            _, gp2 = f.backward(dev(g))
+            assert_same(gp.cpu().numpy(), gp2.cpu().numpy(), "determinism")
+
+
+def test_pre_ops_mean_and_clamp(Q):
+    rng = np.random.default_rng(19)
+    x = (rng.standard_normal(5000) * 2 + 0.3).astype(np.float32)
+    for b in (256, None):
+        # clamp only: bit exact
+        q, _, _ = O.uniform_fwd(x, 16, b, max_element=1.5)
+        qd, _ = Q.uniformQuantization(dev(x), 16, bucket_size=b, max_element=1.5)
+        assert_same(qd.cpu().numpy(), q, "max_element")
+        # mean: the reference's mean is a float32 torch reduction (order dependent) -> tolerance
+        qd, sf = Q.uniformQuantization(dev(x), 16, bucket_size=b, subtract_mean=True)
+        mean = float(sf.mean_tensor)
+        assert abs(mean - x.astype(np.float64).mean()) < 1e-5
+        q2, _, _ = O.uniform_fwd(x - np.float32(mean), 16, b)
+        assert np.abs(qd.cpu().numpy() - (q2 + np.float32(mean))).max() < 1e-5
+
+
+def test_stochastic_rounding_distribution(Q):
+    torch.manual_seed(0)
+    n, s = 1 << 20, 4
+    x = torch.rand(n).cuda()
+    x[0], x[1] = 0.0, 1.0
+    x = x.view(-1)
+    q, sf = Q.uniformQuantization(x, s, stochastic_rounding=True, bucket_size=None)
+    lv = torch.round(q * (s - 1))
+    assert torch.allclose(lv / (s - 1), q, atol=1e-6)
+    lo = torch.floor(x * (s - 1))
+    assert bool(((lv == lo) | (lv == lo + 1)).all())
+    frac = x * (s - 1) - lo
+    up = (lv == lo + 1).float()
+    # E[up] = frac: compare in 10 bins of frac
+    for k in range(10):
+        m = (frac >= k / 10) & (frac < (k + 1) / 10)
+        assert abs(up[m].mean().item() - frac[m].mean().item()) < 0.01
+    q2, _ = Q.uniformQuantization(x, s, stochastic_rounding=True, bucket_size=None)
+    assert not torch.equal(q, q2)                       # a fresh stream per call
+
+
+def test_cpu_tensors_run_on_gpu_and_come_back(Q):
+    rng = np.random.default_rng(23)
+    x = (rng.standard_normal(3000) * 0.05).astype(np.float32)
+    ref, idx, st = O.uniform_fwd(x, 16, 256)
+    q, sf = Q.uniformQuantization(torch.from_numpy(x.copy()), 16, bucket_size=256)
+    assert not q.is_cuda and not sf.alpha.is_cuda
+    assert_same(q.numpy(), ref, "cpu tensor")
+    qn, idxn, _ = Q.nonUniformQuantization(torch.from_numpy(x.copy()), [0.0, 0.3, 0.7, 1.0], bucket_size=256)
+    qo, io, _ = O.nonuniform_fwd(x, np.array([0.0, 0.3, 0.7, 1.0], np.float32), 256)
+    assert_same(qn.numpy(), qo, "cpu nonuniform")
+    assert_same(idxn.numpy(), io, "cpu nonuniform idx")
+
+
+def test_host_buffer_capi_pipeline(Q):
+    from quantized_distillation_b200 import _native as N
+    rng = np.random.default_rng(29)
+    for n, b in ((10_000_003, 256), (5_000_000, 0), (9_000_000, 4096)):
+        x = torch.from_numpy((rng.standard_normal(n) * 0.05).astype(np.float32)).pin_memory()
+        g = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).pin_memory()
+        q = torch.empty(n, dtype=torch.float32).pin_memory()
+        go = torch.empty(n, dtype=torch.float32).pin_memory()
+        N.check(N.lib().qd_uniform_fwd_bwd_host(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, b, 16, N.BWD_TRUNCATED,
+                                                torch.cuda.current_device()))
+        qd, _ = Q.uniformQuantization(x.cuda(), 16, bucket_size=b or None)
+        assert torch.equal(q, qd.cpu()), (n, b)
+        assert torch.equal(go, g)                        # |x| <= 1 everywhere here
+        q.zero_()
+        N.check(N.lib().qd_uniform_fwd_host(N.ptr(x), N.ptr(q), n, b, 16, torch.cuda.current_device()))
+        assert torch.equal(q, qd.cpu())
+
+
+def test_multi_tensor_plan_matches_per_tensor(Q):
+    from quantized_distillation_b200.plan import QuantizationPlan
+    rng = np.random.default_rng(31)
+    sizes = [5000, 10, 5625, 75, 93750, 50, 62500, 50, 31250, 25, 800000, 500, 75, 75, 50, 50, 25, 25, 500, 500, 1, 257]
+    for bucket in (256, 1024, None, 4096):
+        params = [dev((rng.standard_normal(n) * 0.05).astype(np.float32)) for n in sizes]
+        ref = [Q.uniformQuantization(p, 16, bucket_size=bucket)[0] for p in params]
+        plan = QuantizationPlan(params, levels=16, bucket_size=bucket)
+        master = plan.save_master()
+        plan.quantize_()
+        for p, r in zip(params, ref):
+            assert torch.equal(p, r)
+        plan.restore_master()
+        for p, m in zip(params, master):
+            assert torch.equal(p, m)
+        if bucket is not None:
+            grads = [dev(rng.standard_normal(n).astype(np.float32)) for n in sizes]
+            expect = []
+            for p, g in zip(params, grads):
+                f = Q.uniformQuantization_variable(16, bucket_size=bucket)
+                f.forward(p)
+                expect.append(f.backward(g))
+            plan.backward_(grads, "complicated")
+            for g, e in zip(grads, expect):
+                assert torch.equal(g, e)
+
+
+def test_error_mapping(Q):
+    x = torch.randn(100).cuda()
+    with pytest.raises(ValueError):
+        Q.uniformQuantization(x, 1, bucket_size=256)                 # s < 2
+    with pytest.raises(ValueError):
+        Q.ScalingFunction("cubic", False, False, None)
+    with pytest.raises(ValueError):
+        Q.ScalingFunction("linear", False, False, -3)
+    f = Q.uniformQuantization_variable(16, bucket_size=None)
+    f.forward(x)
+    with pytest.raises(NotImplementedError):
+        f.backward(x)
+    with pytest.raises(ValueError):
+        Q.uniformQuantization_variable(16, bucket_size=256).backward(x)
+    with pytest.raises(ValueError):
+        Q.nonUniformQuantization(x, [0.0, 1.0], pre_processed_values=True)
+    with pytest.raises(ValueError):
+        Q.nonUniformQuantization_variable(pre_process_tensors=True)
+    sf = Q.ScalingFunction("linear", False, False, 64)
+    sf.scale_down(x)
+    with pytest.raises(ValueError):
+        sf.inv_scale_down(torch.zeros(3, 64).cuda())
+
+
+def test_division_selftest_on_device(Q):
+    import ctypes as C
+    from quantized_distillation_b200 import _native as N
+    bad = C.c_int64(-1)
+    N.check(N.lib().qd_selftest_division(1 << 26, 1234, C.byref(bad), N.stream_ptr()))
+    assert bad.value == 0
+
+
+def test_full_size_properties_64M(Q):
+    """BASELINE size (64 Mi floats): size-independent properties instead of an oracle run.
+    idempotence (q(q(x)) == q(x)), level count <= s per bucket, range preserved, and the
+    first/last 1 Mi elements against the oracle."""
+    n, s, b = 1 << 26, 16, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, generator=g, device="cuda") * 0.05
+    q, sf = Q.uniformQuantization(x, s, bucket_size=b)
+    q2, _ = Q.uniformQuantization(q, s, bucket_size=b)
+    assert float((q2 - q).abs().max()) <= 1e-6 * float(q.abs().max())
+    rows = q.view(-1, b)
+    assert torch.equal(rows.min(dim=1)[0], x.view(-1, b).min(dim=1)[0])
+    assert float((rows.max(dim=1)[0] - x.view(-1, b).max(dim=1)[0]).abs().max()) <= 1e-6
+    lv = torch.round((rows - sf.beta) / sf.alpha * (s - 1))
+    assert float(lv.min()) == 0 and float(lv.max()) == s - 1
+    for sl in (slice(0, 1 << 20), slice(n - (1 << 20), n)):
+        ref, _, _ = O.uniform_fwd(x[sl].cpu().numpy(), s, b)
+        assert_same(q[sl].cpu().numpy(), ref, "64M slice")
