@@ -88,8 +88,10 @@ def uniform_bwd_minmax(x: torch.Tensor, g: torch.Tensor, s: int, bucket: int):
     amax = (st.argmax + adder).view(-1)
     amin = (st.argmin + adder).view(-1)
     v = g.view(-1) * (qh - (saved.view(-1) - beta) / alpha)
-    owner = torch.arange(n) // row_len
-    r = torch.zeros(rows).index_add_(0, owner, v)
+    # M^T v of the reference (:380-400): per bucket r_b = sum_j v_j, +r_b at argmax', -r_b at argmin'
+    vp = torch.zeros(rows * row_len)
+    vp[0:n] = v
+    r = vp.view(rows, row_len).sum(dim=1)
     corr = torch.zeros(n).index_add_(0, amax, r).index_add_(0, amin, -r)
     return (g.view(-1) + corr).view(g.size())
 

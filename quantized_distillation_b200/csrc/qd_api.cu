@@ -196,10 +196,12 @@ template <int OP, int BWD>
 static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
     if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
     if (P.geo.row_len <= 1024) return launch_warp<OP, BWD>(P, rows_vectorizable(P), s);
-    if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP, BWD>(P, s);
+    // the CTA / grid paths keep stochastic rounding as a run-time branch of OP_UNIFORM
+    constexpr int OP2 = (OP == OP_UNIFORM_STOCH) ? OP_UNIFORM : OP;
+    if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP2, BWD>(P, s);
     if (BWD == BWD_MINMAX)
         return fail(QD_ERR_UNSUPPORTED, "minmax backward needs bucket <= %d (reference: bucket_size None not supported, quant_functions.py:332-334)", QD_MAX_STAGED_BUCKET);
-    return launch_grid<OP, (BWD == BWD_MINMAX ? BWD_OFF : BWD)>(P, ws, ws_bytes, s);
+    return launch_grid<OP2, (BWD == BWD_MINMAX ? BWD_OFF : BWD)>(P, ws, ws_bytes, s);
 }
 
 static Params blank_params() {
@@ -256,6 +258,8 @@ static int uniform_common(Params& P, int64_t n, int64_t bucket, int levels) {
     if (levels < 2) return fail(QD_ERR_INVALID_ARG, "levels (s) must be >= 2, got %d", levels);
     if (geometry_of(n, bucket, &P.geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry n=%lld bucket=%lld", (long long)n, (long long)bucket);
     P.S = (float)(levels - 1);
+    P.rS = 1.0f / P.S;                                    // IEEE division on the host: RN(1/S)
+    P.half_minus_band = 0.5f - P.S * 0x1p-20f;            // see qd_rowops.cuh "fast, still exact, level"
     return QD_OK;
 }
 
@@ -272,6 +276,7 @@ extern "C" int qd_uniform_fwd(const float* x, float* q, uint8_t* idx_u8, float* 
     if (rc) return rc;
     P.x = x; P.q = q; P.idx8 = idx_u8; P.alpha = alpha; P.beta = beta; P.argmin = argmin; P.argmax = argmax;
     P.mean = mean; P.max_element = max_element; P.stochastic = stochastic; P.seed = seed; P.offset = offset;
+    if (stochastic) return run_rows<OP_UNIFORM_STOCH, BWD_OFF>(P, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
     return run_rows<OP_UNIFORM, BWD_OFF>(P, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -474,6 +479,8 @@ extern "C" int qd_plan_create(qd_plan** out, int count, const float* const* src,
         PlanEntry& e = p->host[i];
         e.src = src[i]; e.dst = dst[i]; e.n = n[i]; e.row_start = row; e.rows = g.rows; e.row_len = g.row_len;
         e.S = (float)(levels[i] - 1);
+        e.rS = 1.0f / e.S;
+        e.lim = 0.5f - e.S * 0x1p-20f;
         e.vec = (aligned16(src[i]) && aligned16(dst[i]) && (g.rows == 1 || g.row_len % 4 == 0)) ? 1 : 0;
         row += g.rows;
         if (g.row_len > p->max_row_len) p->max_row_len = g.row_len;

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
         } else if constexpr (OP == OP_UNIFORM) {
             float rb = 0.f;
             int imin2 = 0, imax2 = 0;
+            const UniformFast uf = make_uniform_fast(rs.alpha, P.S);
             if constexpr (BWD == BWD_MINMAX) {
                 float qmn = __int_as_float(0x7f800000), qmx = __int_as_float(0xff800000);
                 for (int e = tid; e < len; e += kBlockCtaThreads) {
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                     uint32_t w = (ge & 3) == 0 ? rnd.x : (ge & 3) == 1 ? rnd.y : (ge & 3) == 2 ? rnd.z : rnd.w;
                     qv = uniform_quantize_stochastic(xv, rs, P.S, u01(w), lvl);
                 } else {
-                    qv = uniform_quantize(xv, rs, P.S, lvl);
+                    qv = uniform_quantize_auto(xv, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
                 }
                 if constexpr (BWD != BWD_OFF) {
                     float gv = P.g[base + e];

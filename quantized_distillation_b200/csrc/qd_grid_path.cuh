@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
         rs.mean = mean;
         rs.alpha = rowstat[row].alpha;
         rs.beta = rowstat[row].beta;
+        const UniformFast uf = make_uniform_fast(rs.alpha, P.S);
         if constexpr (OP == OP_SCALE) {
             // padded layout: positions past the end of the tail row repeat x_hat of the last element
             const int plen = (int)min((int64_t)kGridChunk, P.geo.row_len - off);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                         uint32_t w = (ge & 3) == 0 ? rnd.x : (ge & 3) == 1 ? rnd.y : (ge & 3) == 2 ? rnd.z : rnd.w;
                         qv[j] = uniform_quantize_stochastic(t, rs, P.S, u01(w), lv[j]);
                     } else {
-                        qv[j] = uniform_quantize(t, rs, P.S, lv[j]);
+                        qv[j] = uniform_quantize_auto(t, rs, uf, P.S, P.rS, P.half_minus_band, lv[j]);
                     }
                     if constexpr (BWD == BWD_TRUNC) gv[j] = (fabsf(t) > 1.0f) ? 0.f : gv[j];
                 } else {  // OP_NONUNIFORM

@@ -19,6 +19,8 @@ struct PlanEntry {
     int64_t rows;
     int64_t row_len;
     float S;            // levels - 1
+    float rS;           // RN(1/S)
+    float lim;          // 0.5 - S*2^-20
     int vec;            // 16-byte aligned rows
 };
 
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEn
         P.alpha = nullptr; P.beta = nullptr; P.argmin = nullptr; P.argmax = nullptr;
         P.mean = nullptr; P.max_element = 0.f; P.points = nullptr; P.num_points = 0; P.rule = 0;
         P.geo.n = en.n; P.geo.row_len = en.row_len; P.geo.rows = en.rows;
-        P.S = en.S; P.stochastic = 0; P.seed = 0; P.offset = 0;
+        P.S = en.S; P.rS = en.rS; P.half_minus_band = en.lim; P.stochastic = 0; P.seed = 0; P.offset = 0;
         const int64_t row = grow - en.row_start;
         bool vec = en.vec != 0;
         if constexpr (BWD != BWD_OFF) vec = vec && ((reinterpret_cast<uintptr_t>(P.g) & 15) == 0);

@@ -169,34 +169,61 @@ __device__ __forceinline__ void warp_process_row(const Params& P, const Centroid
         return;
     }
 
+    if constexpr (OP == OP_UNIFORM_STOCH) {
+        float qv[E];
+        float lv[E];
+        Philox rng(P.seed);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            // one Philox block per 4 consecutive elements of the flat tensor
+            if (VEC) {
+                uint4 rnd = rng(P.offset + (uint64_t)((base + elem_index<R, VEC>(r, 0, lane)) >> 2));
+                qv[4 * r + 0] = uniform_quantize_stochastic(v[4 * r + 0], rs, P.S, u01(rnd.x), lv[4 * r + 0]);
+                qv[4 * r + 1] = uniform_quantize_stochastic(v[4 * r + 1], rs, P.S, u01(rnd.y), lv[4 * r + 1]);
+                qv[4 * r + 2] = uniform_quantize_stochastic(v[4 * r + 2], rs, P.S, u01(rnd.z), lv[4 * r + 2]);
+                qv[4 * r + 3] = uniform_quantize_stochastic(v[4 * r + 3], rs, P.S, u01(rnd.w), lv[4 * r + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int64_t ge = base + elem_index<R, VEC>(r, j, lane);
+                    uint4 rnd = rng(P.offset + (uint64_t)(ge >> 2));
+                    uint32_t w = (ge & 3) == 0 ? rnd.x : (ge & 3) == 1 ? rnd.y : (ge & 3) == 2 ? rnd.z : rnd.w;
+                    qv[4 * r + j] = uniform_quantize_stochastic(v[4 * r + j], rs, P.S, u01(w), lv[4 * r + j]);
+                }
+            }
+        }
+        if (pre) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) qv[i] = __fadd_rn(qv[i], rs.mean);
+        }
+        if (P.q != nullptr) store_row<R, VEC, FULL>(P.q + base, len, lane, qv);
+        if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, lv);
+        return;
+    }
+
     if constexpr (OP == OP_UNIFORM) {
         float qv[E];
         float lv[E];
-        if (P.stochastic) {
-            Philox rng(P.seed);
+        const UniformFast uf = make_uniform_fast(rs.alpha, P.S);
+        if (uf.ok) {
+            // fast level (see qd_rowops.cuh): candidates for the whole row, one warp vote, and the
+            // exact IEEE chain only for rows that hold an element near a rounding boundary
+            bool unsafe = false;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                // one Philox block per 4 consecutive elements of the padded layout
-                int e0 = elem_index<R, VEC>(r, 0, lane);
-                if (VEC) {
-                    uint4 rnd = rng(P.offset + (uint64_t)((base + e0) >> 2));
-                    qv[4 * r + 0] = uniform_quantize_stochastic(v[4 * r + 0], rs, P.S, u01(rnd.x), lv[4 * r + 0]);
-                    qv[4 * r + 1] = uniform_quantize_stochastic(v[4 * r + 1], rs, P.S, u01(rnd.y), lv[4 * r + 1]);
-                    qv[4 * r + 2] = uniform_quantize_stochastic(v[4 * r + 2], rs, P.S, u01(rnd.z), lv[4 * r + 2]);
-                    qv[4 * r + 3] = uniform_quantize_stochastic(v[4 * r + 3], rs, P.S, u01(rnd.w), lv[4 * r + 3]);
-                } else {
+            for (int i = 0; i < E; ++i) lv[i] = fast_level(v[i], rs.beta, uf.c, P.half_minus_band, unsafe);
+            if (__any_sync(kFullMask, unsafe)) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        int64_t ge = base + elem_index<R, VEC>(r, j, lane);
-                        uint4 rnd = rng(P.offset + (uint64_t)(ge >> 2));
-                        uint32_t w = (ge & 3) == 0 ? rnd.x : (ge & 3) == 1 ? rnd.y : (ge & 3) == 2 ? rnd.z : rnd.w;
-                        qv[4 * r + j] = uniform_quantize_stochastic(v[4 * r + j], rs, P.S, u01(w), lv[4 * r + j]);
-                    }
-                }
+                for (int i = 0; i < E; ++i) lv[i] = exact_level(v[i], rs.beta, rs.alpha, P.S);
             }
+#pragma unroll
+            for (int i = 0; i < E; ++i) qv[i] = from_unit(small_level_to_unit(lv[i], P.S, P.rS), rs.alpha, rs.beta);
         } else {
 #pragma unroll
-            for (int i = 0; i < E; ++i) qv[i] = uniform_quantize(v[i], rs, P.S, lv[i]);
+            for (int i = 0; i < E; ++i) {
+                const float2 ql = exact_quantize(v[i], rs.beta, rs.alpha, P.S);
+                qv[i] = ql.x;
+                lv[i] = ql.y;
+            }
         }
 
         if constexpr (BWD == BWD_MINMAX) {
@@ -221,12 +248,13 @@ __device__ __forceinline__ void warp_process_row(const Params& P, const Centroid
             int imax = first_equal<R, VEC, FULL>(qv, qmx, len, lane);
             // r_b = sum_j v_j: per-lane float32 partials, float64 across the warp
             double acc = 0.0;
+            const RowDivider div2(rs.alpha2);
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (FULL || elem_index<R, VEC>(r, j, lane) < len)
-                        acc += (double)minmax_term(v[4 * r + j], qv[4 * r + j], gv[4 * r + j], rs);
+                        acc += (double)minmax_term(v[4 * r + j], qv[4 * r + j], gv[4 * r + j], rs.beta2, div2);
             const float rb = (float)warp_sum(acc);
             if (imin != imax) {  // +r at argmax', -r at argmin' (the +1/-1 columns of grad_alpha, :380-393)
 #pragma unroll

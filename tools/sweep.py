@@ -112,5 +112,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--max-log2", type=int, default=28)
+    ap.add_argument("--min-log2", type=int, default=10)
     a = ap.parse_args()
-    print(run(out_path=a.out, max_log2=a.max_log2))
+    print(run(out_path=a.out, max_log2=a.max_log2, min_log2=a.min_log2))
