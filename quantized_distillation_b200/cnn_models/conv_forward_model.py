@@ -1,0 +1,419 @@
+"""CIFAR conv-net and the two training loops that call the quantization hot path
+on every step (reference: cnn_models/conv_forward_model.py):
+
+* ``train_model(quantizeWeights=True)`` -- quantized distillation (:165-393);
+  ``train_model_quantized`` is the alias BASELINE.json's north_star names.
+* ``optimize_quantization_points`` -- differentiable quantization of the
+  centroids (:395-592).
+
+Same keyword arguments and return values as the reference.  What changes is the
+per-step choreography around the model forward/backward: the reference saves
+``state_dict()``, rebinds every ``p.data`` to a freshly quantized tensor (about
+12 launches per tensor) and copies the weights back with ``load_state_dict``;
+here a :class:`QuantizationPlan` snapshots, quantizes IN PLACE and restores all
+tensors with one launch each, which also keeps ``DistributedDataParallel``'s
+parameter references valid.  Unlike the reference (:369-374) exceptions are not
+swallowed.
+"""
+from __future__ import annotations
+
+import copy
+import time
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.optim as optim
+
+from .. import quantization
+from ..plan import QuantizationPlan
+from . import help_fun as cnn_hf
+
+# paper specifications (reference :30-40): teacher ~5.3 M parameters, student ~1 M
+teacherModelSpec = {"spec_conv_layers": [(76, 3, 3), (76, 3, 3), (126, 3, 3), (126, 3, 3), (148, 3, 3), (148, 3, 3),
+                                         (148, 3, 3), (148, 3, 3)],
+                    "spec_max_pooling": [(1, 2, 2), (3, 2, 2), (7, 2, 2)],
+                    "spec_dropout_rates": [(1, 0.2), (3, 0.3), (7, 0.35), (8, 0.4), (9, 0.4)],
+                    "spec_linear": [1200, 1200], "width": 32, "height": 32}
+smallerModelSpec = {"spec_conv_layers": [(75, 5, 5), (50, 5, 5), (50, 5, 5), (25, 5, 5)],
+                    "spec_max_pooling": [(1, 2, 2), (3, 2, 2)],
+                    "spec_dropout_rates": [(1, 0.2), (3, 0.3), (4, 0.4)],
+                    "spec_linear": [500], "width": 32, "height": 32}
+
+
+class ConvolForwardNet(nn.Module):
+    """Stack of same-padded conv layers with max-pooling / dropout inserted at given
+    positions, then linear layers and a 10-way output layer, ReLU everywhere
+    (reference :42-163).
+
+    The output layer is registered BEFORE the layer lists on purpose: that is the
+    reference's registration order (:124-132), so ``parameters()[0]`` is
+    ``out_layer.weight`` and ``quantize_first_and_last_layer=False`` skips the
+    same two tensors as in the reference."""
+
+    def __init__(self, width, height, spec_conv_layers, spec_max_pooling, spec_linear, spec_dropout_rates,
+                 useBatchNorm=False, useAffineTransformInBatchNorm=False):
+        super().__init__()
+        self.width, self.height = width, height
+        self.useBatchNorm = useBatchNorm
+        convs, norms, pools, drops, linears = [], [], [], [], []
+        channels = 3
+        for filters, kh, kw in spec_conv_layers:
+            conv = nn.Conv2d(channels, filters, kernel_size=(kh, kw), padding=((kh - 1) // 2, (kw - 1) // 2))
+            nn.init.xavier_uniform_(conv.weight, nn.init.calculate_gain("conv2d"))
+            convs.append(conv)
+            norms.append(nn.BatchNorm2d(filters, affine=useAffineTransformInBatchNorm))
+            channels = filters
+        self.max_pooling_positions = [pos for pos, _, _ in spec_max_pooling]
+        pools = [nn.MaxPool2d((kh, kw)) for _, kh, kw in spec_max_pooling]
+        self.dropout_positions = [pos for pos, _ in spec_dropout_rates]
+        drops = [nn.Dropout2d(rate) if pos < len(convs) else nn.Dropout(rate) for pos, rate in spec_dropout_rates]
+        features = channels * width * height // 2 ** (2 * len(pools))
+        for units in spec_linear:
+            lin = nn.Linear(features, units)
+            nn.init.xavier_uniform_(lin.weight, nn.init.calculate_gain("linear"))
+            linears.append(lin)
+            norms.append(nn.BatchNorm1d(units, affine=useAffineTransformInBatchNorm))
+            features = units
+        self.out_layer = nn.Linear(features, 10)
+        nn.init.xavier_uniform_(self.out_layer.weight, nn.init.calculate_gain("linear"))
+        self.conv_layers = nn.ModuleList(convs)
+        self.max_pooling_layers = nn.ModuleList(pools)
+        self.dropout_layers = nn.ModuleList(drops)
+        self.linear_layers = nn.ModuleList(linears)
+        self.batchNormalizationLayers = nn.ModuleList(norms)
+        self.num_conv_layers = len(convs)
+        self.total_num_layers = len(convs) + len(linears)
+
+    def forward(self, x):
+        for i in range(self.total_num_layers):
+            if i < self.num_conv_layers:
+                x = F.relu(self.conv_layers[i](x))
+            else:
+                if i == self.num_conv_layers:
+                    x = x.view(x.size(0), -1)
+                x = F.relu(self.linear_layers[i - self.num_conv_layers](x))
+            if self.useBatchNorm:
+                x = self.batchNormalizationLayers[i](x)
+            if i in self.max_pooling_positions:
+                x = self.max_pooling_layers[self.max_pooling_positions.index(i)](x)
+            if i in self.dropout_positions:
+                x = self.dropout_layers[self.dropout_positions.index(i)](x)
+        return F.relu(self.out_layer(x))
+
+
+# ------------------------------------------------------------------------------------------
+# quantized distillation
+# ------------------------------------------------------------------------------------------
+def _selected_parameters(model, quantize_first_and_last_layer):
+    params = list(model.parameters())
+    if quantize_first_and_last_layer is False:
+        params = params[1:-1]                                             # reference :237-239
+    return params
+
+
+def _uniform_levels(quantizationFunctionToUse, numBits):
+    name = quantizationFunctionToUse.lower()
+    if name == "uniformAbsMaxScaling".lower():
+        return 2 ** (numBits - 1), "absmax"                               # reference :206-208 (broken scaling there)
+    if name == "uniformLinearScaling".lower():
+        return 2 ** numBits, "linear"                                     # reference :209-211
+    raise ValueError("The specified quantization function is not present")
+
+
+class WeightQuantizer:
+    """``quantize_weights_model`` / ``backward_quant_weights_model`` of the reference
+    (closures at :235-266) lifted to an object that owns the multi-tensor plan."""
+
+    def __init__(self, model, numBits, bucket_size, quantizationFunctionToUse="uniformLinearScaling",
+                 backprop_quantization_style="none", quantize_first_and_last_layer=True):
+        style = "none" if backprop_quantization_style is None else backprop_quantization_style.lower()
+        if style not in ("none", "truncated", "complicated"):
+            raise ValueError("The specified backprop_quantization_style not recognized")
+        self.style = style
+        self.s, scaling = _uniform_levels(quantizationFunctionToUse, numBits)
+        if scaling != "linear":
+            raise NotImplementedError("absmax scaling does not execute in the reference (quant_functions.py:119-126)")
+        self.params = _selected_parameters(model, quantize_first_and_last_layer)
+        self.plan = QuantizationPlan(self.params, self.s, bucket_size)
+
+    def quantize_weights_model(self, save=True):
+        """fp32 weights -> shadow buffer, then every tensor quantized in place."""
+        if self.style == "truncated":
+            torch._foreach_clamp_min_([p.data for p in self.params], -1.0)   # p.data.clamp_(-1, 1), reference :240-241
+            torch._foreach_clamp_max_([p.data for p in self.params], 1.0)
+        if save:
+            self.plan.save_master()
+        self.plan.quantize_()
+
+    def restore_weights_model(self):
+        self.plan.restore_master()
+
+    def backward_quant_weights_model(self):
+        if self.style == "none":
+            return
+        grads = []
+        for p in self.params:
+            if p.grad is None:
+                raise ValueError("backward_quant_weights_model needs gradients on every quantized parameter")
+            grads.append(p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous())
+        self.plan.backward_(grads, self.style)
+        for p, g in zip(self.params, grads):
+            if g.data_ptr() != p.grad.data_ptr():
+                p.grad.data.copy_(g)
+
+
+def quantize_weights_model(model, numBits, bucket_size=None, quantize_first_and_last_layer=True):
+    """One-shot post-training quantization of a model's weights, in place
+    (what the drivers do tensor by tensor, cifar10_test.py:312-317)."""
+    WeightQuantizer(model, numBits, bucket_size, quantize_first_and_last_layer=quantize_first_and_last_layer) \
+        .quantize_weights_model(save=False)
+    return model
+
+
+def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, use_nesterov=True,
+                initial_momentum=0.9, weight_decayL2=0.00022, epochs_to_train=100, print_every=500,
+                learning_rate_style="generic", use_distillation_loss=False, teacher_model=None,
+                quantizeWeights=False, numBits=8, grad_clipping_threshold=False, start_epoch=0,
+                bucket_size=None, quantizationFunctionToUse="uniformLinearScaling",
+                backprop_quantization_style="none", estimate_quant_grad_every=1, add_gradient_noise=False,
+                ask_teacher_strategy=("always", None), quantize_first_and_last_layer=True,
+                mix_with_differentiable_quantization=False, *, max_steps=None, verbose=True, evaluate=True,
+                step_hook=None):
+    """SGD training with optional distillation loss and optional per-step weight
+    quantization (reference :165-393; same positional/keyword arguments, the
+    keyword-only ones after ``*`` are additions for benchmarking)."""
+    if use_distillation_loss is True and teacher_model is None:
+        raise ValueError("To compute distillation loss you have to pass the teacher model")
+    if teacher_model is not None:
+        teacher_model.eval()
+    learning_rate_style = learning_rate_style.lower()
+    lr_scheduler = cnn_hf.LearningRateScheduler(initial_learning_rate, learning_rate_style)
+    new_learning_rate = initial_learning_rate
+    optimizer = optim.SGD(model.parameters(), lr=initial_learning_rate, nesterov=use_nesterov, momentum=initial_momentum,
+                          weight_decay=weight_decayL2)
+    start_time = time.time()
+    pred_accuracy_epochs, percentages_asked_teacher, losses_epochs = [], [], []
+    informationDict = {}
+    last_loss_saved = float("inf")
+    steps_since_estimate = 1
+    batches_per_epoch = len(train_loader)
+    quantizer = None
+    if quantizeWeights:
+        quantizer = WeightQuantizer(model, numBits, bucket_size, quantizationFunctionToUse, backprop_quantization_style,
+                                    quantize_first_and_last_layer)
+    if print_every > batches_per_epoch:
+        print_every = max(batches_per_epoch // 2, 1)
+    total_steps = 0
+    stop = False
+    epoch = start_epoch
+    try:
+        for epoch in range(start_epoch, epochs_to_train + start_epoch):
+            model.train()
+            running = torch.zeros((), device=cnn_hf._device_of(model))
+            asked, seen = 0, 0
+            for idx_minibatch, data in enumerate(train_loader, start=1):
+                quantize_now = quantizer is not None and steps_since_estimate >= estimate_quant_grad_every
+                if quantize_now:
+                    quantizer.quantize_weights_model()                    # :286-287
+                model.zero_grad(set_to_none=False)
+                loss, c_teach, c_total = cnn_hf.forward_and_backward(
+                    model, data, idx_minibatch, epoch, use_distillation_loss=use_distillation_loss,
+                    teacher_model=teacher_model, ask_teacher_strategy=ask_teacher_strategy, return_more_info=True,
+                    return_tensor=True)
+                asked += c_teach
+                seen += c_total
+                if quantize_now:
+                    quantizer.restore_weights_model()                     # :302
+                if add_gradient_noise and not quantizeWeights:
+                    cnn_hf.add_gradient_noise(model, idx_minibatch, epoch, batches_per_epoch)
+                if grad_clipping_threshold is not False:
+                    for p in model.parameters():
+                        if p.grad is not None:
+                            p.grad.clamp_(-grad_clipping_threshold, grad_clipping_threshold)
+                if quantize_now:
+                    quantizer.backward_quant_weights_model()              # :315
+                optimizer.step()
+                if steps_since_estimate >= estimate_quant_grad_every:
+                    steps_since_estimate = 0
+                steps_since_estimate += 1
+                running += loss
+                total_steps += 1
+                if step_hook is not None:
+                    step_hook(total_steps, loss)
+                if idx_minibatch % print_every == 0:
+                    last_loss_saved = float(running.item()) / print_every
+                    running.zero_()
+                    if verbose:
+                        msg = "Time Elapsed: {:.1f}s, [Start Epoch: {}, Epoch: {}, Minibatch: {}], loss: {:3f}".format(
+                            time.time() - start_time, start_epoch + 1, epoch + 1, idx_minibatch, last_loss_saved)
+                        if pred_accuracy_epochs:
+                            msg += " Last prediction accuracy: {:2f}%".format(pred_accuracy_epochs[-1] * 100)
+                        print(msg)
+                if max_steps is not None and total_steps >= max_steps:
+                    stop = True
+                    break
+            percentages_asked_teacher.append(asked / seen if seen else 0)
+            losses_epochs.append(last_loss_saved)
+            if evaluate:
+                pred_accuracy_epochs.append(cnn_hf.evaluateModel(model, test_loader, fastEvaluation=False))
+                if verbose:
+                    print(" === Epoch: {} - prediction accuracy {:2f}% === ".format(epoch + 1, pred_accuracy_epochs[-1] * 100))
+            if stop:
+                break
+            if mix_with_differentiable_quantization and epoch != start_epoch + epochs_to_train - 1:
+                state = optimize_quantization_points(
+                    model, train_loader, test_loader, new_learning_rate, initial_momentum=initial_momentum,
+                    epochs_to_train=1, print_every=print_every, use_nesterov=use_nesterov,
+                    learning_rate_style=learning_rate_style, numPointsPerTensor=2 ** numBits,
+                    assignBitsAutomatically=True, bucket_size=bucket_size, use_distillation_loss=True,
+                    initialize_method="quantiles", quantize_first_and_last_layer=quantize_first_and_last_layer,
+                    verbose=verbose, evaluate=evaluate)[0]
+                model.load_state_dict(state)
+                losses_epochs.append(last_loss_saved)
+                if evaluate:
+                    pred_accuracy_epochs.append(cnn_hf.evaluateModel(model, test_loader, fastEvaluation=False))
+            error = 1 - pred_accuracy_epochs[-1] if pred_accuracy_epochs else 1.0
+            new_learning_rate, stop_training = lr_scheduler.update_learning_rate(epoch, error)
+            if stop_training is True:
+                break
+            for group in optimizer.param_groups:
+                group["lr"] = new_learning_rate
+    except KeyboardInterrupt:
+        informationDict["errorFlag"] = False
+        informationDict["numEpochsTrained"] = epoch - start_epoch
+    else:
+        informationDict["errorFlag"] = False
+        informationDict["numEpochsTrained"] = epoch + 1 - start_epoch
+    if quantizer is not None:
+        quantizer.quantize_weights_model(save=False)                       # final weights are returned quantized (:384-385)
+    if mix_with_differentiable_quantization:
+        informationDict["numEpochsTrained"] *= 2
+    informationDict["percentages_asked_teacher"] = percentages_asked_teacher
+    informationDict["predictionAccuracy"] = pred_accuracy_epochs
+    informationDict["lossSaved"] = losses_epochs
+    informationDict["numStepsTrained"] = total_steps
+    return model, informationDict
+
+
+def train_model_quantized(model, train_loader, test_loader, numBits=8, bucket_size=None, **kwargs):
+    """``train_model(..., quantizeWeights=True)``: the entry point BASELINE.json's
+    north_star names (the reference spells it through the ``quantizeWeights`` flag)."""
+    return train_model(model, train_loader, test_loader, quantizeWeights=True, numBits=numBits, bucket_size=bucket_size,
+                       **kwargs)
+
+
+# ------------------------------------------------------------------------------------------
+# differentiable quantization
+# ------------------------------------------------------------------------------------------
+def optimize_quantization_points(modelToQuantize, train_loader, test_loader, initial_learning_rate=1e-5,
+                                 initial_momentum=0.9, epochs_to_train=30, print_every=500, use_nesterov=True,
+                                 learning_rate_style="generic", numPointsPerTensor=16, assignBitsAutomatically=False,
+                                 bucket_size=None, use_distillation_loss=True, initialize_method="quantiles",
+                                 quantize_first_and_last_layer=True, *, max_steps=None, verbose=True, evaluate=True,
+                                 step_hook=None):
+    """Learn the quantization points of every tensor by SGD on the loss of the
+    quantized network, the unquantized network acting as teacher (reference
+    :395-592).  Returns ``(quantizedModel.state_dict(), pointsPerTensor, informationDict)``."""
+    numTensorsNetwork = sum(1 for _ in modelToQuantize.parameters())
+    initialize_method = initialize_method.lower()
+    if initialize_method not in ("quantiles", "uniform"):
+        raise ValueError("The initialization method must be either quantiles or uniform")
+    if isinstance(numPointsPerTensor, int):
+        numPointsPerTensor = [numPointsPerTensor] * numTensorsNetwork
+    if len(numPointsPerTensor) != numTensorsNetwork:
+        raise ValueError("numPointsPerTensor must be equal to the number of tensor in the network")
+    if quantize_first_and_last_layer is False:
+        numPointsPerTensor = numPointsPerTensor[1:-1]
+    device = cnn_hf._device_of(modelToQuantize)
+    scalingFunction = quantization.ScalingFunction("linear", False, False, bucket_size, False)     # :420
+
+    if assignBitsAutomatically:                                             # :424-448
+        num_to_estimate_grad = 5
+        modelToQuantize.zero_grad()
+        for idx_minibatch, batch in enumerate(train_loader, start=1):
+            cnn_hf.forward_and_backward(modelToQuantize, batch, idx_batch=idx_minibatch, epoch=0,
+                                        use_distillation_loss=False, return_tensor=True)
+            if idx_minibatch >= num_to_estimate_grad:
+                break
+        norms = [float((p.grad / num_to_estimate_grad).norm())
+                 for p in _selected_parameters(modelToQuantize, quantize_first_and_last_layer)]
+        modelToQuantize.zero_grad()
+        numPointsPerTensor = quantization.help_functions.assign_bits_automatically(norms, numPointsPerTensor,
+                                                                                   input_is_point=True)
+
+    selected = _selected_parameters(modelToQuantize, quantize_first_and_last_layer)
+    pointsPerTensor = []
+    for p, num in zip(selected, numPointsPerTensor):                          # :451-482
+        if initialize_method == "quantiles":
+            init = quantization.help_functions.initialize_quantization_points(p.data, scalingFunction, num)
+        else:
+            init = torch.tensor([x / (num - 1) for x in range(num)], dtype=torch.float32, device=device)
+        init = init.to(device).clone().requires_grad_(True)
+        init.grad = torch.zeros_like(init)
+        pointsPerTensor.append(init)
+
+    options = {"momentum": initial_momentum, "nesterov": use_nesterov} if initial_momentum != 0 else {}
+    optimizer = optim.SGD(pointsPerTensor, lr=initial_learning_rate, **options)
+    lr_scheduler = cnn_hf.LearningRateScheduler(initial_learning_rate, learning_rate_style)
+    start_time = time.time()
+    pred_accuracy_epochs, losses_epochs = [], []
+    last_loss_saved = float("inf")
+    batches_per_epoch = len(train_loader)
+    if print_every > batches_per_epoch:
+        print_every = max(batches_per_epoch // 2, 1)
+
+    modelToQuantize.eval()
+    quantizedModel = copy.deepcopy(modelToQuantize)                           # :497-498
+    q_selected = _selected_parameters(quantizedModel, quantize_first_and_last_layer)
+    quantizationFunctions = [quantization.nonUniformQuantization_variable(
+        max_element=False, subtract_mean=False, modify_in_place=False, bucket_size=bucket_size,
+        pre_process_tensors=True, tensor=p.data) for p in q_selected]         # :501-511
+
+    total_steps, epoch, stop = 0, 0, False
+    for epoch in range(epochs_to_train):
+        quantizedModel.train()
+        running = torch.zeros((), device=device)
+        for idx_minibatch, data in enumerate(train_loader, start=1):
+            quantizedModel.zero_grad(set_to_none=False)
+            optimizer.zero_grad(set_to_none=False)
+            for fun, p_q, pts in zip(quantizationFunctions, q_selected, pointsPerTensor):   # :525-532
+                fun.forward(None, pts.data, out=p_q.data)
+            loss = cnn_hf.forward_and_backward(quantizedModel, data, idx_minibatch, epoch,
+                                               use_distillation_loss=use_distillation_loss,
+                                               teacher_model=modelToQuantize, return_tensor=True)
+            for fun, p_q, pts in zip(quantizationFunctions, q_selected, pointsPerTensor):   # :539-545
+                pts.grad.data = fun.backward(p_q.grad.data)[1]
+            optimizer.step()
+            for pts in pointsPerTensor:                                       # :550-551
+                pts.data = torch.sort(pts.data)[0]
+            running += loss
+            total_steps += 1
+            if step_hook is not None:
+                step_hook(total_steps, loss)
+            if idx_minibatch % print_every == 0:
+                last_loss_saved = float(running.item()) / print_every
+                running.zero_()
+                if verbose:
+                    print("Time Elapsed: {:.1f}s, [Epoch: {}, Minibatch: {}], loss: {:3f}".format(
+                        time.time() - start_time, epoch + 1, idx_minibatch, last_loss_saved))
+            if max_steps is not None and total_steps >= max_steps:
+                stop = True
+                break
+        losses_epochs.append(last_loss_saved)
+        if evaluate:
+            pred_accuracy_epochs.append(cnn_hf.evaluateModel(quantizedModel, test_loader, fastEvaluation=False))
+            if verbose:
+                print(" === Epoch: {} - prediction accuracy {:2f}% === ".format(epoch + 1, pred_accuracy_epochs[-1] * 100))
+        if stop:
+            break
+        error = 1 - pred_accuracy_epochs[-1] if pred_accuracy_epochs else 1.0
+        new_learning_rate, stop_training = lr_scheduler.update_learning_rate(epoch, error)
+        if stop_training is True:
+            break
+        for group in optimizer.param_groups:
+            group["lr"] = new_learning_rate
+    informationDict = {"predictionAccuracy": pred_accuracy_epochs, "numEpochsTrained": epoch + 1,
+                       "lossSaved": losses_epochs, "numStepsTrained": total_steps}
+    # the state dict also carries the batch-norm running statistics of the quantized model (:579-592)
+    return quantizedModel.state_dict(), pointsPerTensor, informationDict

@@ -195,7 +195,7 @@ static bool rows_vectorizable(const Params& P) {
 template <int OP, int BWD>
 static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
     if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
-    if (P.geo.row_len <= 1024) return launch_warp<OP, BWD>(P, rows_vectorizable(P), s);
+    if (P.geo.row_len <= 1024) return launch_warp<OP, (OP == OP_NONUNIFORM ? 0 : BWD)>(P, rows_vectorizable(P), s);
     // the CTA / grid paths keep stochastic rounding as a run-time branch of OP_UNIFORM
     constexpr int OP2 = (OP == OP_UNIFORM_STOCH) ? OP_UNIFORM : OP;
     if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP2, BWD>(P, s);
@@ -335,7 +335,14 @@ extern "C" int qd_nonuniform_fwd(const float* x, const float* points, int num_po
     if (geometry_of(n, bucket, &P.geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry n=%lld bucket=%lld", (long long)n, (long long)bucket);
     P.x = x; P.q = q; P.idx8 = idx_u8; P.idx64 = idx_i64; P.alpha = alpha; P.beta = beta;
     P.points = points; P.num_points = num_points; P.rule = rule; P.mean = mean; P.max_element = max_element;
-    return run_rows<OP_NONUNIFORM, BWD_OFF>(P, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (P.geo.row_len <= 1024) {  // warp path: short centroid tables live in registers (AUX = table size)
+        const bool vec = rows_vectorizable(P);
+        if (num_points <= 4) return launch_warp<OP_NONUNIFORM, 4>(P, vec, s);
+        if (num_points <= 8) return launch_warp<OP_NONUNIFORM, 8>(P, vec, s);
+        return launch_warp<OP_NONUNIFORM, 0>(P, vec, s);
+    }
+    return run_rows<OP_NONUNIFORM, BWD_OFF>(P, workspace, workspace_bytes, s);
 }
 
 extern "C" int qd_nonuniform_bwd(const float* g, const uint8_t* idx_u8, const int64_t* idx_i64, const float* alpha,
@@ -349,7 +356,7 @@ extern "C" int qd_nonuniform_bwd(const float* g, const uint8_t* idx_u8, const in
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    const int64_t items = geo.rows * ((geo.row_len + kPgItem - 1) / kPgItem);
+    const int64_t items = (geo.n + kPgTile - 1) / kPgTile + geo.rows;  // upper bound of warp work items
     int64_t need_ctas = (items + kPgWarps - 1) / kPgWarps;
     int64_t cap = (int64_t)di->sms * 8;
     if (cap > (int64_t)kPointsGradMaxCtas) cap = kPointsGradMaxCtas;
@@ -581,6 +588,14 @@ __global__ void selftest_division_kernel(int64_t pairs, uint64_t seed, unsigned 
         double qd = (double)a / (double)d;  // exact to 53 bits; rounding to 24 is then correct
         float qr = (float)qd;               // unless qd sits within 2^-29 rel. of a tie (never for 24-bit a, d)
         if (q != qr) atomicAdd(mismatches, 1ull);
+        // hoisted-reciprocal division used by the kernels, incl. its guard and slow path
+        const RowDivider div(d);
+        if (div.exact(a) != q) atomicAdd(mismatches, 1ull);
+        float tiny = __fmul_rn(a, (r.w & 1u) ? 0x1p-28f : 0x1p-33f);  // around and below the guard threshold
+        if (div.exact(tiny) != __fdiv_rn(tiny, d)) atomicAdd(mismatches, 1ull);
+        // level / S for S <= 255
+        const float S = (float)(1u + (r.w >> 8) % 255u), k = (float)((r.w >> 16) % ((unsigned)S + 1u));
+        if (small_level_to_unit(k, S, __fdiv_rn(1.0f, S)) != __fdiv_rn(k, S)) atomicAdd(mismatches, 1ull);
     }
 }
 

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEn
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
     Centroids cen{nullptr, nullptr, 0};
+    RegTable<0> rt;
     for (int64_t grow = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); grow < total_rows; grow += stride) {
         int lo = 0, hi = count - 1;  // largest t with row_start[t] <= grow
         while (lo < hi) {
@@ -61,10 +62,10 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEn
         if constexpr (BWD != BWD_OFF) vec = vec && ((reinterpret_cast<uintptr_t>(P.g) & 15) == 0);
         if (vec) {
             const bool full = (en.row_len == R * 128) && ((row + 1) * en.row_len <= en.n);
-            if (full) warp_process_row<OP_UNIFORM, BWD, R, true, true>(P, cen, row, lane);
-            else warp_process_row<OP_UNIFORM, BWD, R, true, false>(P, cen, row, lane);
+            if (full) warp_process_row<OP_UNIFORM, BWD, R, true, true>(P, cen, rt, row, lane);
+            else warp_process_row<OP_UNIFORM, BWD, R, true, false>(P, cen, rt, row, lane);
         } else {
-            warp_process_row<OP_UNIFORM, BWD, R, false, false>(P, cen, row, lane);
+            warp_process_row<OP_UNIFORM, BWD, R, false, false>(P, cen, rt, row, lane);
         }
     }
 }

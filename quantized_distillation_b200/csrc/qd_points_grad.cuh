@@ -4,12 +4,15 @@
 //     grad_points[k] = sum_{i : idx_i = k} fl32(g_i * alpha_row(i))
 //
 // The reference makes K masked passes over the tensor; here it is one pass,
-// 5 B/elt (float32 g + uint8 idx).  Work item = up to 1024 consecutive elements
-// of one row (so alpha is a per-item scalar), one warp per item, float64
-// accumulators in registers for 8 centroids at a time.  Reduction order is
-// fixed (lane tree -> warps in order -> CTAs in order), so the result is
-// deterministic and data-parallel replicas stay bit-identical without any
-// communication.
+// 5 B/elt (float32 g + uint8 idx).  Scatter-by-index without atomics: every lane
+// owns a private column of K float32 bins in shared memory, laid out
+// bins[k][lane] so that a warp's 32 read-modify-writes always hit 32 distinct
+// banks whatever the indices are.  Per element that is one LDS, one FADD and
+// one STS, independent of K (K <= 32 per sweep; larger K re-sweeps the data).
+// Columns are flushed to float64 every 64 tiles, so float32 only ever adds a
+// few thousand terms; the float64 reduction order is fixed (lane tree -> warps
+// in order -> CTAs in order): the result is deterministic, which keeps
+// data-parallel replicas bit-identical without communication.
 #pragma once
 #include "qd_common.cuh"
 
@@ -17,61 +20,98 @@ namespace qd {
 
 constexpr int kPgThreads = 256;
 constexpr int kPgWarps = kPgThreads / 32;
-constexpr int kPgItem = 1024;
-constexpr int kPgGroup = 8;  // centroids accumulated per sweep
+constexpr int kPgTile = 1024;      // elements per warp work item
+constexpr int kPgSweep = 32;       // centroids handled per sweep over the data
+constexpr int kPgFlushEvery = 64;  // tiles between float32 -> float64 flushes
 
 template <typename IdxT>
 __global__ void __launch_bounds__(kPgThreads) points_grad_partial(const float* __restrict__ g,
                                                                  const IdxT* __restrict__ idx,
                                                                  const float* __restrict__ alpha, int K, Geometry geo,
                                                                  double* __restrict__ partial /*[gridDim.x][K]*/) {
+    __shared__ float s_col[kPgWarps][kPgSweep][32];
     extern __shared__ double s_acc[];  // [kPgWarps][K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kPgWarps * K; i += kPgThreads) s_acc[i] = 0.0;
     __syncthreads();
+    float(*col)[32] = s_col[warp];
 
-    const int64_t items_per_row = (geo.row_len + kPgItem - 1) / kPgItem;
-    const int64_t items = geo.rows * items_per_row;
+    // tile mode: 1024 consecutive elements of the flat tensor, alpha uniform per 128-element chunk
+    const bool tile_mode = (geo.rows == 1) || (geo.row_len % 128 == 0);
+    const int64_t tiles_per_row = (geo.row_len + kPgTile - 1) / kPgTile;
+    const int64_t items = tile_mode ? (geo.n + kPgTile - 1) / kPgTile : geo.rows * tiles_per_row;
     const int64_t stride = (int64_t)gridDim.x * kPgWarps;
-    for (int kg = 0; kg < K; kg += kPgGroup) {
-        double acc[kPgGroup];
-#pragma unroll
-        for (int k = 0; k < kPgGroup; ++k) acc[k] = 0.0;
+    const bool vec_ok = sizeof(IdxT) == 1 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(idx) & 3) == 0);
+
+    for (int kg = 0; kg < K; kg += kPgSweep) {
+        const int kcount = min(kPgSweep, K - kg);
+        for (int k = 0; k < kcount; ++k) col[k][lane] = 0.f;
+        __syncwarp();
+        int since_flush = 0;
         for (int64_t item = (int64_t)blockIdx.x * kPgWarps + warp; item < items; item += stride) {
-            const int64_t row = item / items_per_row, sub = item % items_per_row;
-            const int64_t start = row * geo.row_len + sub * kPgItem;
-            const int64_t row_end = min((row + 1) * geo.row_len, geo.n);
-            const int len = (int)min((int64_t)kPgItem, row_end - start);
-            if (len <= 0) continue;
-            const float a = alpha[row];
-            const float* gp = g + start;
-            const IdxT* ip = idx + start;
-            const bool vec = sizeof(IdxT) == 1 && ((reinterpret_cast<uintptr_t>(gp) & 15) == 0) &&
-                             ((reinterpret_cast<uintptr_t>(ip) & 3) == 0);
-            const int vlen = vec ? (len & ~3) : 0;
-            for (int e = lane * 4; e < vlen; e += 128) {
-                float4 t = *reinterpret_cast<const float4*>(gp + e);
-                uint32_t w = *reinterpret_cast<const uint32_t*>(ip + e);
-                float pv[4] = {__fmul_rn(t.x, a), __fmul_rn(t.y, a), __fmul_rn(t.z, a), __fmul_rn(t.w, a)};
+            if (tile_mode) {
+                const int64_t start = item * kPgTile;
+                const int len = (int)min((int64_t)kPgTile, geo.n - start);
+                if (vec_ok && len == kPgTile) {
+                    float4 gv[8];
+                    uint32_t iw[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int id = (int)((w >> (8 * j)) & 0xffu) - kg;
+                    for (int j = 0; j < 8; ++j) {  // all 16 loads in flight before the first use
+                        gv[j] = ld_stream4(g + start + j * 128 + lane * 4);
+                        iw[j] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(idx) + start + j * 128 + lane * 4);
+                    }
+                    // row of each 128-element chunk: one division per tile, then increments
+                    int64_t row = (geo.rows == 1) ? 0 : start / geo.row_len;
+                    int64_t rem = (geo.rows == 1) ? 0 : start - row * geo.row_len;
 #pragma unroll
-                    for (int k = 0; k < kPgGroup; ++k) acc[k] += (id == k) ? (double)pv[j] : 0.0;
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = alpha[row];
+                        if (geo.rows != 1) {
+                            rem += 128;
+                            if (rem >= geo.row_len) { rem -= geo.row_len; ++row; }
+                        }
+                        const float pv[4] = {__fmul_rn(gv[j].x, a), __fmul_rn(gv[j].y, a), __fmul_rn(gv[j].z, a),
+                                             __fmul_rn(gv[j].w, a)};  // in-place multiply of the reference (:495)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const unsigned id = ((iw[j] >> (8 * c)) & 0xffu) - (unsigned)kg;
+                            if (id < (unsigned)kcount) col[id][lane] += pv[c];
+                        }
+                    }
+                } else {
+                    for (int e = lane; e < len; e += 32) {
+                        const int64_t ge = start + e;
+                        const float a = (geo.rows == 1) ? alpha[0] : alpha[ge / geo.row_len];
+                        const unsigned id = (unsigned)idx[ge] - (unsigned)kg;
+                        if (id < (unsigned)kcount) col[id][lane] += __fmul_rn(g[ge], a);
+                    }
+                }
+            } else {
+                const int64_t row = item / tiles_per_row, sub = item % tiles_per_row;
+                const int64_t start = row * geo.row_len + sub * kPgTile;
+                const int64_t row_end = min((row + 1) * geo.row_len, geo.n);
+                const int len = (int)min((int64_t)kPgTile, row_end - start);
+                const float a = alpha[row];
+                for (int e = lane; e < len; e += 32) {
+                    const unsigned id = (unsigned)idx[start + e] - (unsigned)kg;
+                    if (id < (unsigned)kcount) col[id][lane] += __fmul_rn(g[start + e], a);
                 }
             }
-            for (int e = vlen + lane; e < len; e += 32) {
-                const float pv = __fmul_rn(gp[e], a);  // in-place multiply of the reference (:495)
-                const int id = (int)ip[e] - kg;
-#pragma unroll
-                for (int k = 0; k < kPgGroup; ++k) acc[k] += (id == k) ? (double)pv : 0.0;
+            if (++since_flush == kPgFlushEvery) {
+                since_flush = 0;
+                for (int k = 0; k < kcount; ++k) {
+                    const double s = warp_sum((double)col[k][lane]);
+                    col[k][lane] = 0.f;
+                    if (lane == 0) s_acc[warp * K + kg + k] += s;
+                }
             }
         }
-#pragma unroll
-        for (int k = 0; k < kPgGroup; ++k) {
-            double s = warp_sum(acc[k]);
-            if (lane == 0 && kg + k < K) s_acc[warp * K + kg + k] = s;
+        for (int k = 0; k < kcount; ++k) {
+            const double s = warp_sum((double)col[k][lane]);
+            if (lane == 0) s_acc[warp * K + kg + k] += s;
         }
+        __syncwarp();
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += kPgThreads) {
@@ -81,11 +121,15 @@ __global__ void __launch_bounds__(kPgThreads) points_grad_partial(const float* _
     }
 }
 
-__global__ void points_grad_final(const double* __restrict__ partial, int nblocks, int K, float* __restrict__ out) {
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+// one warp per centroid: lanes stride over the CTA partials, then a fixed shuffle tree
+__global__ void __launch_bounds__(256) points_grad_final(const double* __restrict__ partial, int nblocks, int K,
+                                                         float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < K; k += (int)(blockDim.x >> 5)) {
         double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * K + k];
-        out[k] = (float)s;
+        for (int b = lane; b < nblocks; b += 32) s += partial[(int64_t)b * K + k];
+        s = warp_sum(s);
+        if (lane == 0) out[k] = (float)s;
     }
 }
 

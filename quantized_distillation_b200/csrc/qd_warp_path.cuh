@@ -92,8 +92,32 @@ __device__ __forceinline__ int first_equal(const float (&v)[4 * R], float target
 
 // One row, one warp.  OP / BWD / WANT_* are compile-time so the hot forward
 // kernel carries no dead code.
-template <int OP, int BWD, int R, bool VEC, bool FULL>
-__device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen, int64_t row, int lane) {
+template <int R, bool VEC, bool FULL>
+__device__ __forceinline__ void store_row_u8(uint8_t* __restrict__ p, int len, int lane, const int (&lv)[4 * R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (VEC && (FULL || r * 128 + lane * 4 + 4 <= len) && ((reinterpret_cast<uintptr_t>(p) & 3) == 0)) {
+            uint32_t w = (uint32_t)lv[4 * r] | ((uint32_t)lv[4 * r + 1] << 8) | ((uint32_t)lv[4 * r + 2] << 16) |
+                         ((uint32_t)lv[4 * r + 3] << 24);
+            *reinterpret_cast<uint32_t*>(p + r * 128 + lane * 4) = w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int e = elem_index<R, VEC>(r, j, lane);
+                if (e < len) p[e] = (uint8_t)lv[4 * r + j];
+            }
+        }
+    }
+}
+
+// AUX is the backward mode for OP_UNIFORM and the register-table size KR (0 = table in
+// shared memory) for OP_NONUNIFORM.
+template <int OP, int AUX, int R, bool VEC, bool FULL>
+__device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen,
+                                                 const RegTable<(OP == OP_NONUNIFORM ? AUX : 0)>& rt, int64_t row,
+                                                 int lane) {
+    constexpr int BWD = (OP == OP_UNIFORM) ? AUX : (int)BWD_OFF;
+    constexpr int KR = (OP == OP_NONUNIFORM) ? AUX : 0;
     constexpr int E = 4 * R;
     const int64_t base = row * P.geo.row_len;
     const int len = FULL ? R * 128 : (int)min(P.geo.row_len, P.geo.n - base);
@@ -285,38 +309,46 @@ __device__ __forceinline__ void warp_process_row(const Params& P, const Centroid
 
     if constexpr (OP == OP_NONUNIFORM) {
         float qv[E];
-        float lv[E];
+        int li[E];
+        const RowDivider div(rs.alpha);
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            float xh = to_unit(v[i], rs.beta, rs.alpha);
-            int id = centroid_index(cen, xh, P.rule);
-            lv[i] = (float)id;
-            qv[i] = from_unit(cen.k[id], rs.alpha, rs.beta);
+            const float xh = div.exact(__fsub_rn(v[i], rs.beta));       // == to_unit(), bit for bit
+            float kval;
+            if constexpr (KR > 0) {
+                li[i] = rt.index(xh, P.rule, cen.K, kval);
+            } else {
+                li[i] = centroid_index(cen, xh, P.rule);
+                kval = cen.k[li[i]];
+            }
+            qv[i] = from_unit(kval, rs.alpha, rs.beta);
             if (pre) qv[i] = __fadd_rn(qv[i], rs.mean);
         }
         if (P.q != nullptr) store_row<R, VEC, FULL>(P.q + base, len, lane, qv);
-        if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, lv);
+        if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, li);
         if (P.idx64 != nullptr) {
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     int e = elem_index<R, VEC>(r, j, lane);
-                    if (FULL || e < len) P.idx64[base + e] = (int64_t)lv[4 * r + j];
+                    if (FULL || e < len) P.idx64[base + e] = (int64_t)li[4 * r + j];
                 }
         }
         return;
     }
 }
 
-template <int OP, int BWD, int R, bool VEC>
+template <int OP, int AUX, int R, bool VEC>
 __global__ void __launch_bounds__(kWarpCtaThreads) warp_rows_kernel(const __grid_constant__ Params P) {
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
     __shared__ float s_m[OP == OP_NONUNIFORM ? 256 : 1];
     Centroids cen{s_k, s_m, P.num_points};
+    RegTable<(OP == OP_NONUNIFORM ? AUX : 0)> rt;
     if constexpr (OP == OP_NONUNIFORM) {
         centroid_setup(s_k, s_m, P.points, P.num_points);
         __syncthreads();
+        rt.load(cen);
     }
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
@@ -324,9 +356,9 @@ __global__ void __launch_bounds__(kWarpCtaThreads) warp_rows_kernel(const __grid
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < P.geo.rows; row += stride) {
         const bool full = row_is_full && ((row + 1) * P.geo.row_len <= P.geo.n);
         if (full)
-            warp_process_row<OP, BWD, R, VEC, VEC>(P, cen, row, lane);  // FULL only exists for VEC
+            warp_process_row<OP, AUX, R, VEC, VEC>(P, cen, rt, row, lane);  // FULL only exists for VEC
         else
-            warp_process_row<OP, BWD, R, VEC, false>(P, cen, row, lane);
+            warp_process_row<OP, AUX, R, VEC, false>(P, cen, rt, row, lane);
     }
 }
 

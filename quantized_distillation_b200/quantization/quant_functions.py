@@ -416,9 +416,14 @@ class nonUniformQuantization_variable(object):
             self._search_sorted_obj = SearchSorted(sf.scale_down(self._tensor).view(-1))
         return self._search_sorted_obj
 
-    def _fused_forward(self, x, points, rule, sf):
+    def _fused_forward(self, x, points, rule, sf, out=None):
         pts = _points_tensor(points, x.device)
-        q = torch.empty_like(x)
+        if out is not None:
+            if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x.numel()):
+                raise ValueError("out must be a contiguous float32 CUDA tensor with as many elements as the input")
+            q = out
+        else:
+            q = torch.empty_like(x)
         idx = torch.empty(x.numel(), dtype=torch.uint8, device=x.device)
         b = _bucket_arg(self.bucket_size)
         ws = N.workspace(x.numel(), b, x.device)
@@ -428,7 +433,9 @@ class nonUniformQuantization_variable(object):
                                           N.stream_ptr(x.device)))
         return q, idx
 
-    def forward(self, inputTensor, listQuantizationPoints):
+    def forward(self, inputTensor, listQuantizationPoints, out=None):
+        """``out`` (extension): write the quantized tensor straight into an existing
+        tensor, e.g. the live parameter, instead of allocating a new one."""
         if listQuantizationPoints.dim() != 1:                                            # :451-452
             raise ValueError("listPoints must be a 1-D tensor")
         numPoints = listQuantizationPoints.size()[0]
@@ -443,7 +450,7 @@ class nonUniformQuantization_variable(object):
             sf.original_tensor_size = inputTensor.size()
             sf._prepare(x, want_arg=False)
             rule, shape = N.RULE_NEAREST, inputTensor.size()
-        q, idx = self._fused_forward(x, listQuantizationPoints, rule, sf)
+        q, idx = self._fused_forward(x, listQuantizationPoints, rule, sf, out=out)
         self.savedForBackward = {"indices": idx.view(shape), "numPoints": numPoints, "scalingFactor": sf.alpha}   # :467-468
         q = q.view(shape)
         return q.cpu() if was_cpu else q

@@ -1,0 +1,167 @@
+"""GPU tests of the callers of the hot path: the quantized-distillation loop and the
+differentiable-quantization loop (reference: cnn_models/conv_forward_model.py:165-592)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import quantized_distillation_b200.quantization as Q
+    from quantized_distillation_b200.cnn_models import conv_forward_model as cfm
+    from quantized_distillation_b200.cnn_models import help_fun as hf
+    return Q, cfm, hf
+
+
+def make_student(cfm):
+    spec = dict(cfm.smallerModelSpec)
+    spec["spec_dropout_rates"] = []
+    return cfm.ConvolForwardNet(**spec, useBatchNorm=True, useAffineTransformInBatchNorm=True).cuda()
+
+
+def distinct_per_bucket(t, bucket):
+    flat = t.detach().view(-1)
+    n = flat.numel()
+    worst = 0
+    for start in range(0, n, bucket):
+        worst = max(worst, int(torch.unique(flat[start:start + bucket]).numel()))
+    return worst
+
+
+def test_weight_quantizer_matches_reference_choreography(env):
+    """quantize -> restore -> gradient fix-up of the plan == the reference's per-tensor loop
+    (conv_forward_model.py:236-266, 286, 302) done with the per-tensor API."""
+    Q, cfm, hf = env
+    torch.manual_seed(0)
+    for first_last in (True, False):
+        model = make_student(cfm)
+        original = [p.detach().clone() for p in model.parameters()]
+        wq = cfm.WeightQuantizer(model, numBits=4, bucket_size=256, backprop_quantization_style="complicated",
+                                 quantize_first_and_last_layer=first_last)
+        wq.quantize_weights_model()
+        n_params = len(original)
+        for i, (p, o) in enumerate(zip(model.parameters(), original)):
+            if first_last is False and i in (0, n_params - 1):
+                assert torch.equal(p, o)                              # skipped tensors untouched
+            else:
+                assert torch.equal(p, Q.uniformQuantization(o, 16, bucket_size=256)[0])
+        wq.restore_weights_model()
+        for p, o in zip(model.parameters(), original):
+            assert torch.equal(p, o)
+        for p in model.parameters():
+            p.grad = torch.randn_like(p)
+        grads = [p.grad.clone() for p in model.parameters()]
+        wq.backward_quant_weights_model()
+        for i, (p, o, g) in enumerate(zip(model.parameters(), original, grads)):
+            if first_last is False and i in (0, n_params - 1):
+                assert torch.equal(p.grad, g)
+            else:
+                f = Q.uniformQuantization_variable(16, bucket_size=256)
+                f.forward(o)
+                assert torch.equal(p.grad, f.backward(g))
+
+
+@pytest.mark.parametrize("style", ["none", "truncated", "complicated"])
+def test_quantized_distillation_runs_and_returns_quantized_weights(env, style):
+    Q, cfm, hf = env
+    torch.manual_seed(0)
+    student = make_student(cfm)
+    teacher = make_student(cfm).eval()
+    data = hf.synthetic_cifar_loader(6, 25, seed=1)
+    before = [p.detach().clone() for p in student.parameters()]
+    losses = []
+    model, info = cfm.train_model_quantized(student, data, data, numBits=4, bucket_size=256, use_distillation_loss=True,
+                                            teacher_model=teacher, epochs_to_train=1, print_every=2, verbose=False,
+                                            backprop_quantization_style=style, quantize_first_and_last_layer=False,
+                                            step_hook=lambda i, l: losses.append(l))
+    assert info["numStepsTrained"] == 6 and info["errorFlag"] is False
+    assert all(torch.isfinite(l) for l in losses)
+    params = list(model.parameters())
+    assert any(not torch.equal(a, b) for a, b in zip(params, before))       # it trained
+    for i, p in enumerate(params[1:-1], start=1):                            # final weights are quantized (:385)
+        assert distinct_per_bucket(p, 256) <= 16, i
+    assert distinct_per_bucket(params[0], 256) > 16                          # first tensor was skipped
+
+
+def test_one_step_equals_manual_reference_step(env):
+    """A full train_model step equals: quantize every tensor with the per-tensor API, forward/backward,
+    restore, SGD -- the reference's step (:280-317) -- up to cuDNN's run-to-run float noise."""
+    Q, cfm, hf = env
+    torch.backends.cudnn.deterministic = True
+    torch.manual_seed(3)
+    a = make_student(cfm)
+    b = make_student(cfm)
+    b.load_state_dict(a.state_dict())
+    teacher = make_student(cfm).eval()
+    data = hf.synthetic_cifar_loader(1, 25, seed=5)
+    cfm.train_model_quantized(a, data, data, numBits=4, bucket_size=256, use_distillation_loss=True, teacher_model=teacher,
+                              epochs_to_train=1, print_every=1, verbose=False, evaluate=False, max_steps=1)
+    # manual step on b
+    opt = torch.optim.SGD(b.parameters(), lr=0.001, nesterov=True, momentum=0.9, weight_decay=0.00022)
+    b.train()
+    saved = [p.detach().clone() for p in b.parameters()]
+    for p in b.parameters():
+        p.data = Q.uniformQuantization(p.data, 16, bucket_size=256)[0]
+    b.zero_grad()
+    hf.forward_and_backward(b, data[0], 1, 0, use_distillation_loss=True, teacher_model=teacher)
+    for p, s in zip(b.parameters(), saved):
+        p.data = s
+    opt.step()
+    for p in b.parameters():                                                 # train_model returns quantized weights
+        p.data = Q.uniformQuantization(p.data, 16, bucket_size=256)[0]
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=0, atol=float(pb.abs().max()) * 0.08 + 1e-6)
+        assert (pa != pb).float().mean() < 0.02                               # at most a few level flips from float noise
+    torch.backends.cudnn.deterministic = False
+
+
+def test_differentiable_quantization_loop(env):
+    Q, cfm, hf = env
+    torch.manual_seed(0)
+    model = make_student(cfm)
+    data = hf.synthetic_cifar_loader(6, 25, seed=2)
+    state, points, info = cfm.optimize_quantization_points(
+        model, data, data, initial_learning_rate=1e-3, epochs_to_train=1, print_every=2, numPointsPerTensor=4,
+        bucket_size=256, use_distillation_loss=True, initialize_method="quantiles", verbose=False)
+    assert info["numStepsTrained"] == 6 and len(points) == 22
+    sf = Q.ScalingFunction("linear", False, False, 256, False)
+    for p, (name, w) in zip(points, [(k, v) for k, v in state.items() if k in dict(model.named_parameters())]):
+        assert p.numel() == 4 and bool((p[1:] >= p[:-1]).all())                # kept sorted (:550-551)
+    # quantized model weights only take centroid values (in scaled space) of their tensor
+    params = dict(model.named_parameters())
+    checked = 0
+    for (name, p0), pts in zip(params.items(), points):
+        wq = state[name]
+        f = Q.nonUniformQuantization_variable(bucket_size=256, pre_process_tensors=True, tensor=p0.data)
+        # the loop wrote forward(points BEFORE the last update); check the invariant instead: <= 4 values per bucket
+        assert distinct_per_bucket(wq, 256) <= 4, name
+        checked += 1
+    assert checked == 22
+    # uniform initialisation + automatic bit assignment path
+    state, points, info = cfm.optimize_quantization_points(
+        model, data, data, initial_learning_rate=1e-3, epochs_to_train=1, print_every=2, numPointsPerTensor=4,
+        bucket_size=256, use_distillation_loss=True, initialize_method="uniform", assignBitsAutomatically=True,
+        quantize_first_and_last_layer=False, verbose=False, max_steps=2, evaluate=False)
+    assert len(points) == 20 and sum(p.numel() for p in points) == 80
+    with pytest.raises(ValueError):
+        cfm.optimize_quantization_points(model, data, data, initialize_method="kmeans")
+
+
+def test_wide_resnet_quantized_step(env):
+    Q, cfm, hf = env
+    from quantized_distillation_b200.cnn_models.wide_resnet import Wide_ResNet
+    torch.manual_seed(0)
+    student = Wide_ResNet(depth=10, widen_factor=2, dropout_rate=0.3, num_classes=10).cuda()
+    teacher = Wide_ResNet(depth=10, widen_factor=2, dropout_rate=0.0, num_classes=10).cuda().eval()
+    data = hf.synthetic_cifar_loader(3, 16, seed=3)
+    model, info = cfm.train_model_quantized(student, data, data, numBits=2, bucket_size=256, use_distillation_loss=True,
+                                            teacher_model=teacher, initial_learning_rate=0.1, weight_decayL2=5e-4,
+                                            learning_rate_style="cifar100", epochs_to_train=1, print_every=1, verbose=False,
+                                            quantize_first_and_last_layer=False)
+    assert info["numStepsTrained"] == 3
+    params = list(model.parameters())
+    assert distinct_per_bucket(params[5], 256) <= 4

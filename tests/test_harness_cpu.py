@@ -1,0 +1,135 @@
+"""Host-side checks of the training harness (no GPU): model shapes the hot path sees,
+loss formula, schedules, and the N>1 data-parallel plumbing on gloo with world_size 2."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+from quantized_distillation_b200.cnn_models import conv_forward_model as cfm
+from quantized_distillation_b200.cnn_models import help_fun as hf
+from quantized_distillation_b200.cnn_models.wide_resnet import Wide_ResNet
+
+
+def student():
+    spec = dict(cfm.smallerModelSpec)
+    spec["spec_dropout_rates"] = []
+    return cfm.ConvolForwardNet(**spec, useBatchNorm=True, useAffineTransformInBatchNorm=True)
+
+
+def test_student_parameter_list_matches_survey():
+    m = student()
+    sizes = [p.numel() for p in m.parameters()]
+    assert len(sizes) == 22 and sum(sizes) == 1_000_235
+    assert sizes[0] == 5000 and sizes[1] == 10                     # out_layer registered first
+    assert sizes[2] == 5625 and sizes[10] == 800_000
+    sel = cfm._selected_parameters(m, False)
+    assert len(sel) == 20 and sel[0].numel() == 10
+    teacher = cfm.ConvolForwardNet(**cfm.teacherModelSpec, useBatchNorm=True, useAffineTransformInBatchNorm=True)
+    assert sum(p.numel() for p in teacher.parameters()) == 5_346_142
+
+
+def test_wrn_16_22_parameter_list_matches_survey():
+    m = Wide_ResNet(depth=16, widen_factor=22, dropout_rate=0.3, num_classes=10)
+    sizes = [p.numel() for p in m.parameters()]
+    assert len(sizes) == 60 and sum(sizes) == 82_746_890
+    assert sizes[0] == 432 and sizes[-1] == 10 and max(sizes) == 17_842_176
+    with pytest.raises(ValueError):
+        Wide_ResNet(depth=17, widen_factor=2, dropout_rate=0.0, num_classes=10)
+
+
+def test_forward_shapes_and_distillation_loss_formula():
+    torch.manual_seed(0)
+    m = student()
+    x = torch.randn(4, 3, 32, 32)
+    y = torch.randint(0, 10, (4,))
+    assert m(x).shape == (4, 10)
+    out, t_out = torch.randn(4, 10), torch.randn(4, 10)
+    T = 2
+    kl = F.kl_div(F.log_softmax(out / T, dim=1), F.softmax(t_out / T, dim=1), reduction="sum") / out.numel()
+    expect = 0.7 * T * T * kl + 0.3 * F.cross_entropy(out, y)
+    assert torch.allclose(hf.distillation_loss(out, y, t_out), expect)
+    teacher = student().eval()
+    loss, asked, total = hf.forward_and_backward(m, (x, y), 1, 0, use_distillation_loss=True, teacher_model=teacher,
+                                                 return_more_info=True)
+    assert isinstance(loss, float) and asked == 4 and total == 4
+    assert all(p.grad is not None for p in m.parameters())
+    with pytest.raises(ValueError):
+        hf.forward_and_backward(m, (x, y), 1, 0, use_distillation_loss=True)
+    for strat in (("incorrect_labels", None), ("cutoff_entropy", 1.0), ("random_entropy", None)):
+        m.zero_grad()
+        hf.forward_and_backward(m, (x, y), 1, 0, use_distillation_loss=True, teacher_model=teacher, ask_teacher_strategy=strat)
+
+
+def test_learning_rate_schedules():
+    s = hf.LearningRateScheduler(0.1, "cifar100")
+    assert s.update_learning_rate(10, 0.5)[0] == 0.1
+    assert abs(s.update_learning_rate(61, 0.5)[0] - 0.02) < 1e-12
+    assert abs(s.update_learning_rate(161, 0.5)[0] - 0.1 * 0.2 ** 3) < 1e-12
+    g = hf.LearningRateScheduler(1.0, "generic")
+    lr = 1.0
+    for epoch in range(12):
+        lr, stop = g.update_learning_rate(epoch, 0.5)
+    assert lr == 0.5 and stop is False
+    with pytest.raises(ValueError):
+        hf.LearningRateScheduler(0.1, "cosine")
+
+
+def test_train_model_without_quantization_runs_on_cpu():
+    torch.manual_seed(0)
+    m = student()
+    data = hf.synthetic_cifar_loader(3, 4, pin=False)
+    model, info = cfm.train_model(m, data, data, epochs_to_train=1, print_every=1, verbose=False)
+    assert info["numStepsTrained"] == 3 and info["errorFlag"] is False and len(info["predictionAccuracy"]) == 1
+    with pytest.raises(ValueError):
+        cfm.train_model(m, data, data, use_distillation_loss=True)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _ddp_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from quantized_distillation_b200 import distributed as D
+    w, r, device = D.init_distributed(backend="gloo")
+    torch.manual_seed(1234)                                        # same init on every rank
+    model = D.wrap_ddp(student(), device)
+    global_batches = hf.synthetic_cifar_loader(2, 8, seed=7, pin=False)
+    local = D.shard_batches(global_batches, r, w)
+    assert local[0][0].size(0) == 4
+    cfm.train_model(model, local, local, epochs_to_train=1, print_every=1, verbose=False, evaluate=False)
+    flat = torch.cat([p.detach().view(-1) for p in model.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(w)]
+    torch.distributed.all_reduce(flat.clone())                     # exercises the collective path
+    torch.distributed.all_gather(gathered, flat)
+    ret[rank] = bool(torch.equal(gathered[0], gathered[1]))
+    assert D.max_over_ranks(float(r), device) == w - 1
+    torch.distributed.destroy_process_group()
+
+
+def test_ddp_replicas_stay_identical_gloo_world2():
+    """N>1 path on CPU: two gloo ranks, sharded global batch, DDP gradient all-reduce;
+    after training the replicas hold bit-identical parameters."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ddp_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret[0] is True and ret[1] is True
+
+
+def test_state_dict_prefix_helpers():
+    from quantized_distillation_b200 import distributed as D
+    sd = student().state_dict()
+    wrapped = D.convert_state_dict_to_data_parallel(sd)
+    assert all(k.startswith("module.") for k in wrapped)
+    assert list(D.convert_state_dict_from_data_parallel(wrapped)) == list(sd)
+    with pytest.raises(ValueError):
+        D.shard_batches([(torch.zeros(5, 3), torch.zeros(5))], 0, 2)
