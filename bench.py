@@ -114,12 +114,57 @@ def physical_gpu_index(local_rank: int) -> int:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_port_throughput(n: int, repeats: int, warmup: int):
-    """The reference's CPU path for one fwd+bwd (oracle/torch_chain.py, same torch ops,
-    all host threads).  Returns (GB/s at 16 B/elt, seconds per pass, threads)."""
+def usable_cpus() -> int:
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:                                            # cgroup v2 quota, if any
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+_BEST_THREADS = None
+
+
+def best_cpu_threads() -> int:
+    """All the host threads the reference's torch ops can USE: torch's intra-op pool is tried at
+    1, 2, 4, ... up to the usable CPU count on a small sample and the fastest setting is kept
+    (on a container whose CPU quota is below the visible core count, more threads is slower)."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
     import torch
     from oracle import torch_chain as T
-    threads = os.cpu_count() or 1
+    cap = usable_cpus()
+    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, cap) if c <= cap})
+    x = torch.randn(1 << 20) * 0.05
+    g = torch.randn(1 << 20)
+    timing = {}
+    for c in cands:
+        torch.set_num_threads(c)
+        best = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            T.uniform_fwd(x, LEVELS, BUCKET)
+            T.uniform_bwd_minmax(x, g, LEVELS, BUCKET)
+            best = min(best, time.perf_counter() - t0)
+        timing[c] = best
+    _BEST_THREADS = min(timing, key=timing.get)
+    torch.set_num_threads(_BEST_THREADS)
+    return _BEST_THREADS
+
+
+def cpu_port_throughput(n: int, repeats: int, warmup: int):
+    """The reference's CPU path for one fwd+bwd (oracle/torch_chain.py, same torch ops,
+    best thread count on this host).  Returns (GB/s at 16 B/elt, seconds per pass, threads)."""
+    import torch
+    from oracle import torch_chain as T
+    threads = best_cpu_threads()
     torch.set_num_threads(threads)
     g0 = torch.Generator().manual_seed(0)
     x = torch.randn(n, generator=g0) * 0.05
@@ -146,7 +191,8 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3 * (N_ELEMS / CPU_SAMPLE_ELEMS), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
+                         "host_cpus_visible": os.cpu_count(), "host_cpus_usable": usable_cpus()},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -160,6 +206,81 @@ def workload_config(n_gpus):
             "l2_policy": "inputs+outputs are 1 GiB per step, larger than the 126 MB L2; no flush needed"}
 
 
+# ----------------------------------------------------------------------------- training legs
+def run_train_leg(kind, world, rank, dev, steps, warmup):
+    """CIFAR10-shaped quantized distillation steps/s (BASELINE configs 2-4), synthetic data,
+    random-init weights.  Every step copies its batch from pinned host memory and reads the
+    loss back (print_every=1), so the number is end to end.  DDP when world > 1."""
+    import torch
+    import torch.distributed as dist
+    from quantized_distillation_b200 import distributed as D
+    from quantized_distillation_b200.cnn_models import conv_forward_model as cfm
+    from quantized_distillation_b200.cnn_models import help_fun as hf
+    from quantized_distillation_b200.cnn_models.wide_resnet import Wide_ResNet
+
+    torch.manual_seed(1234)
+    if kind in ("student", "diffquant"):
+        spec = dict(cfm.smallerModelSpec)
+        spec["spec_dropout_rates"] = []
+        student = cfm.ConvolForwardNet(**spec, useBatchNorm=True, useAffineTransformInBatchNorm=True).to(dev)
+        teacher = cfm.ConvolForwardNet(**cfm.teacherModelSpec, useBatchNorm=True, useAffineTransformInBatchNorm=True).to(dev).eval()
+        per_gpu_batch, bits = 25, 4
+        kw = dict(initial_learning_rate=1e-3, weight_decayL2=2.2e-4)
+        name = "ConvolForwardNet smallerModelSpec (22 tensors, 1,000,235 params), teacher teacherModelSpec"
+    else:
+        student = Wide_ResNet(depth=16, widen_factor=22, dropout_rate=0.3, num_classes=10).to(dev)
+        teacher = Wide_ResNet(depth=28, widen_factor=20, dropout_rate=0.3, num_classes=10).to(dev).eval()
+        per_gpu_batch, bits = (100 // world if 100 % world == 0 else 13), 2
+        kw = dict(initial_learning_rate=0.1, weight_decayL2=5e-4, learning_rate_style="cifar100", quantize_first_and_last_layer=False)
+        name = "Wide_ResNet-16-22 student (60 tensors, 82,746,890 params), WRN-28-20 teacher"
+    total = warmup + steps
+    data = hf.synthetic_cifar_loader(total, per_gpu_batch, seed=100 + rank)
+    ev = {}
+
+    def hook(i, loss):
+        if i == warmup:
+            ev["t0"] = torch.cuda.Event(enable_timing=True)
+            ev["t0"].record()
+        if i == total:
+            ev["t1"] = torch.cuda.Event(enable_timing=True)
+            ev["t1"].record()
+
+    if kind == "diffquant":
+        cfm.optimize_quantization_points(student, data, data, initial_learning_rate=1e-5, epochs_to_train=1, print_every=1,
+                                         numPointsPerTensor=4, bucket_size=256, use_distillation_loss=True,
+                                         initialize_method="quantiles", verbose=False, evaluate=False, max_steps=total,
+                                         step_hook=hook)
+        label = "differentiable quantization, 4 centroids per tensor, bucket 256 (BASELINE config 4)"
+    else:
+        model = D.wrap_ddp(student, dev)
+        cfm.train_model_quantized(model, data, data, numBits=bits, bucket_size=256, use_distillation_loss=True,
+                                  teacher_model=teacher, epochs_to_train=1, print_every=1, verbose=False, evaluate=False,
+                                  max_steps=total, step_hook=hook, **kw)
+        label = f"{bits}-bit quantized distillation, bucket 256 (BASELINE config {2 if kind == 'student' else 3})"
+    torch.cuda.synchronize(dev)
+    ms = ev["t0"].elapsed_time(ev["t1"]) / steps
+    ms = D.max_over_ranks(ms, dev)
+    return {"config": f"{label}; {name}; per-GPU batch {per_gpu_batch}, global batch {per_gpu_batch * world}, "
+                      f"{'DDP+NCCL' if world > 1 else 'single process'}, synthetic CIFAR-shaped data, loss read back every step",
+            "steps_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 3), "images_per_s": round(per_gpu_batch * world * 1e3 / ms, 1),
+            "steps": steps, "warmup": warmup, "n_gpus": world}
+
+
+def cpu_model_quant_ms(sizes, levels, bucket, repeats=3):
+    """The reference's per-step quantization loop on the host (conv_forward_model.py:236-247):
+    one op chain per parameter tensor (oracle/torch_chain.py)."""
+    import torch
+    from oracle import torch_chain as T
+    torch.set_num_threads(best_cpu_threads())
+    params = [torch.randn(n) * 0.05 for n in sizes]
+    best = float("inf")
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        T.quantize_model_step(params, levels, bucket)
+        best = min(best, time.perf_counter() - t0)
+    return best * 1e3
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -170,6 +291,9 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="also print the per-size / per-op table (profiles/)")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--train", default="student", choices=["none", "student", "wrn", "diffquant"],
+                    help="also report CIFAR10-shaped quantized-distillation steps/s (BASELINE configs 2/3/4)")
+    ap.add_argument("--train-steps", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -287,7 +411,14 @@ def main():
         gbs, sec, threads = cpu_port_throughput(CPU_SAMPLE_ELEMS, 3, 1)
         out["cpu_baseline"] = {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port",
                                "sample": f"{CPU_SAMPLE_ELEMS} of {N_ELEMS} elements (1/16), best of 3, oracle/torch_chain.py "
-                                         "(the reference's torch op chain; /root/reference is absent on the GPU box)"}
+                                         "(the reference's torch op chain; /root/reference is absent on the GPU box); "
+                                         "thread count auto-tuned over powers of two up to the usable CPUs",
+                               "host_cpus_visible": os.cpu_count(), "host_cpus_usable": usable_cpus()}
+    if args.train != "none":
+        out["train"] = run_train_leg(args.train, world, rank, dev, args.train_steps, 8)
+        if rank == 0 and world == 1 and not args.no_cpu and args.train == "student":
+            sizes = [5000, 10, 5625, 75, 93750, 50, 62500, 50, 31250, 25, 800000, 500] + [75, 75, 50, 50, 50, 50, 25, 25, 500, 500]
+            out["train"]["cpu_reference_quantize_ms_per_step"] = round(cpu_model_quant_ms(sizes, 16, 256), 3)
     if args.sweep and rank == 0:
         from tools import sweep
         out["sweep_file"] = sweep.run(dev)

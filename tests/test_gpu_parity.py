@@ -468,3 +468,24 @@ def test_full_size_properties_64M(Q):
     for sl in (slice(0, 1 << 20), slice(n - (1 << 20), n)):
         ref, _, _ = O.uniform_fwd(x[sl].cpu().numpy(), s, b)
         assert_same(q[sl].cpu().numpy(), ref, "64M slice")
+    # the whole 64 Mi tensor, bit for bit, against the C restatement (oracle/quant_oracle.c)
+    from oracle import c_oracle as CO
+    xh = x.cpu().numpy()
+    qc, idxc, stc = CO.uniform_fwd(xh, s, b)
+    assert_same(q.cpu().numpy(), qc, "64M full tensor vs C oracle")
+    assert_same(sf.alpha.view(-1).cpu().numpy(), stc["alpha"], "64M alpha")
+    assert_same(sf.idx_max_rows.view(-1).cpu().numpy(), stc["argmax"], "64M argmax")
+    del qc, idxc
+    # fused forward+backward at full size: q identical, gout within the float32-sum tolerance per bucket
+    from quantized_distillation_b200 import _native as N
+    gd = torch.randn(n, generator=g, device="cuda")
+    qq, go = torch.empty_like(x), torch.empty_like(gd)
+    ws = N.workspace(n, b, x.device)
+    N.check(N.lib().qd_uniform_fwd_bwd(N.ptr(x), N.ptr(gd), N.ptr(qq), N.ptr(go), n, b, s, N.BWD_MINMAX, N.ptr(ws), ws.numel(),
+                                       N.stream_ptr()))
+    assert torch.equal(qq, q)
+    ref = CO.uniform_bwd_minmax(xh, gd.cpu().numpy(), s, b)
+    diff = np.abs(go.cpu().numpy().astype(np.float64) - ref)
+    changed = np.nonzero(go.cpu().numpy() != gd.cpu().numpy())[0]
+    assert changed.size <= 2 * (n // b) and np.array_equal(changed, np.nonzero(ref != gd.cpu().numpy())[0])
+    assert diff.max() <= 1e-4, diff.max()

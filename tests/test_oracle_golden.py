@@ -135,3 +135,32 @@ def test_torch_chain_matches_golden(golden):
         gout = T.uniform_bwd_minmax(torch.from_numpy(data[k + "_x"].copy()), torch.from_numpy(data[k + "_g"].copy()),
                                     c["s"], c["bucket"])
         assert np.abs(gout.numpy() - data[k + "_gout"]).max() <= 1e-6 * np.abs(data[k + "_g"]).sum() / c["s"] + 1e-7
+
+
+def test_c_oracle_matches_golden(golden):
+    """oracle/quant_oracle.c (gcc, -ffp-contract=off) reproduces the reference bit for bit."""
+    from oracle import c_oracle as CO
+    data, cases = golden
+    for c in cases["uniform"]:
+        k = c["key"]
+        q, idx, st = CO.uniform_fwd(data[k + "_x"], c["s"], c["bucket"])
+        eq(q, data[k + "_q"].reshape(-1))
+        eq(st["alpha"], data[k + "_alpha"])
+        eq(st["argmin"], data[k + "_argmin"])
+        eq(st["argmax"], data[k + "_argmax"])
+        eq(idx, data[k + "_idx_rint"])
+    for c in cases["nonuniform"]:
+        k = c["key"]
+        q, idx, st = CO.nonuniform_fwd(data[k + "_x"], data[k + "_points"], c["bucket"], "nearest")
+        eq(q, data[k + "_q_nearest"].reshape(-1))
+        eq(idx, data[k + "_idx_nearest"].reshape(-1))
+        q, idx, st = CO.nonuniform_fwd(data[k + "_x"], data[k + "_points2"], c["bucket"], "midpoint")
+        eq(q, data[k + "_q_midpoint2"].reshape(-1))
+        eq(idx, data[k + "_idx_midpoint2"].reshape(-1))
+        gp = CO.nonuniform_bwd_points(data[k + "_g"], idx, st["alpha"], data[k + "_points"].size, c["bucket"])
+        scale = np.abs(data[k + "_g"]).astype(np.float64).sum() * float(st["alpha"].max())
+        assert np.abs(gp - data[k + "_gpoints2"]).max() <= 1e-6 * scale + 1e-12
+    for c in cases["minmax_bwd"]:
+        k = c["key"]
+        out = CO.uniform_bwd_minmax(data[k + "_x"], data[k + "_g"], c["s"], c["bucket"])
+        assert np.abs(out - data[k + "_gout"]).max() <= 1e-6 * np.abs(data[k + "_g"]).sum() / c["s"] + 1e-7
