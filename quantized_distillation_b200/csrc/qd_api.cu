@@ -195,7 +195,7 @@ static bool rows_vectorizable(const Params& P) {
 template <int OP, int BWD>
 static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
     if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
-    if (P.geo.row_len <= 1024) return launch_warp<OP, (OP == OP_NONUNIFORM ? 0 : BWD)>(P, rows_vectorizable(P), s);
+    if (P.geo.row_len <= 1024) return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
     // the CTA / grid paths keep stochastic rounding as a run-time branch of OP_UNIFORM
     constexpr int OP2 = (OP == OP_UNIFORM_STOCH) ? OP_UNIFORM : OP;
     if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP2, BWD>(P, s);
@@ -340,7 +340,9 @@ extern "C" int qd_nonuniform_fwd(const float* x, const float* points, int num_po
         const bool vec = rows_vectorizable(P);
         if (num_points <= 4) return launch_warp<OP_NONUNIFORM, 4>(P, vec, s);
         if (num_points <= 8) return launch_warp<OP_NONUNIFORM, 8>(P, vec, s);
-        return launch_warp<OP_NONUNIFORM, 0>(P, vec, s);
+        if (num_points <= 16) return launch_warp<OP_NONUNIFORM, 16>(P, vec, s);   // unrolled search in shared memory
+        if (num_points <= 64) return launch_warp<OP_NONUNIFORM, 64>(P, vec, s);
+        return launch_warp<OP_NONUNIFORM, 256>(P, vec, s);
     }
     return run_rows<OP_NONUNIFORM, BWD_OFF>(P, workspace, workspace_bytes, s);
 }

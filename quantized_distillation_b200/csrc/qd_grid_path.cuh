@@ -165,6 +165,44 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                             reinterpret_cast<uintptr_t>(P.g + g0) | reinterpret_cast<uintptr_t>(P.gout + g0)) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(P.idx8 + g0) & 3) == 0);
         const int vlen = vec ? (len & ~3) : 0;
+        if constexpr (OP == OP_UNIFORM) {
+            // hot case: a complete, aligned chunk of the plain uniform op -- four float4 loads per
+            // thread in flight before the first use, streaming stores
+            if (vec && len == kGridChunk && !P.stochastic && P.idx8 == nullptr && P.idx64 == nullptr && !pre) {
+                constexpr int kPer = 4;
+#pragma unroll 1
+                for (int it = 0; it < kGridChunk / (kGridCtaThreads * 4 * kPer); ++it) {
+                    float4 xv4[kPer], gv4[kPer];
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) {
+                        const int e = (it * kPer + u) * (kGridCtaThreads * 4) + threadIdx.x * 4;
+                        xv4[u] = ld_stream4(P.x + g0 + e);
+                        if constexpr (BWD != BWD_OFF) gv4[u] = ld_stream4(P.g + g0 + e);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) {
+                        const int e = (it * kPer + u) * (kGridCtaThreads * 4) + threadIdx.x * 4;
+                        float lvl;
+                        float4 qo;
+                        qo.x = uniform_quantize_auto(xv4[u].x, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+                        qo.y = uniform_quantize_auto(xv4[u].y, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+                        qo.z = uniform_quantize_auto(xv4[u].z, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+                        qo.w = uniform_quantize_auto(xv4[u].w, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+                        if (P.q != nullptr) st_stream4(P.q + g0 + e, qo);
+                        if constexpr (BWD != BWD_OFF) {
+                            if constexpr (BWD == BWD_TRUNC) {
+                                gv4[u].x = (fabsf(xv4[u].x) > 1.0f) ? 0.f : gv4[u].x;
+                                gv4[u].y = (fabsf(xv4[u].y) > 1.0f) ? 0.f : gv4[u].y;
+                                gv4[u].z = (fabsf(xv4[u].z) > 1.0f) ? 0.f : gv4[u].z;
+                                gv4[u].w = (fabsf(xv4[u].w) > 1.0f) ? 0.f : gv4[u].w;
+                            }
+                            st_stream4(P.gout + g0 + e, gv4[u]);
+                        }
+                    }
+                }
+                continue;
+            }
+        }
         for (int e0 = threadIdx.x * 4; e0 < len; e0 += kGridCtaThreads * 4) {
             const bool v4 = e0 + 4 <= vlen;
             const int cnt = min(4, len - e0);

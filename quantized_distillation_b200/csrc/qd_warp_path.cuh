@@ -113,20 +113,23 @@ __device__ __forceinline__ void store_row_u8(uint8_t* __restrict__ p, int len, i
 // AUX is the backward mode for OP_UNIFORM and the register-table size KR (0 = table in
 // shared memory) for OP_NONUNIFORM.
 template <int OP, int AUX, int R, bool VEC, bool FULL>
-__device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen,
-                                                 const RegTable<(OP == OP_NONUNIFORM ? AUX : 0)>& rt, int64_t row,
-                                                 int lane) {
+__device__ __forceinline__ void warp_load_row(const Params& P, int64_t row, int lane, float (&v)[4 * R], float (&gv)[4 * R]) {
+    constexpr int BWD = (OP == OP_UNIFORM) ? AUX : (int)BWD_OFF;
+    const int64_t base = row * P.geo.row_len;
+    const int len = FULL ? R * 128 : (int)min(P.geo.row_len, P.geo.n - base);
+    load_row<R, VEC, FULL>(P.x + base, len, lane, v);
+    if constexpr (BWD != BWD_OFF) load_row<R, VEC, FULL>(P.g + base, len, lane, gv);
+}
+
+template <int OP, int AUX, int R, bool VEC, bool FULL>
+__device__ __forceinline__ void warp_compute_row(const Params& P, const Centroids& cen,
+                                                 const RegTable<(OP == OP_NONUNIFORM && AUX <= 8 ? AUX : 0)>& rt, int64_t row,
+                                                 int lane, float (&v)[4 * R], float (&gv)[4 * R]) {
     constexpr int BWD = (OP == OP_UNIFORM) ? AUX : (int)BWD_OFF;
     constexpr int KR = (OP == OP_NONUNIFORM) ? AUX : 0;
     constexpr int E = 4 * R;
     const int64_t base = row * P.geo.row_len;
     const int len = FULL ? R * 128 : (int)min(P.geo.row_len, P.geo.n - base);
-
-    float v[E];
-    load_row<R, VEC, FULL>(P.x + base, len, lane, v);
-
-    float gv[E];
-    if constexpr (BWD != BWD_OFF) load_row<R, VEC, FULL>(P.g + base, len, lane, gv);
 
     RowState rs;
     rs.mean = 0.f;
@@ -315,7 +318,9 @@ __device__ __forceinline__ void warp_process_row(const Params& P, const Centroid
         for (int i = 0; i < E; ++i) {
             const float xh = div.exact(__fsub_rn(v[i], rs.beta));       // == to_unit(), bit for bit
             float kval;
-            if constexpr (KR > 0) {
+            if constexpr (KR > 8) {
+                li[i] = smem_index<KR>(cen.k, cen.m, cen.K, xh, P.rule, kval);
+            } else if constexpr (KR > 0) {
                 li[i] = rt.index(xh, P.rule, cen.K, kval);
             } else {
                 li[i] = centroid_index(cen, xh, P.rule);
@@ -339,12 +344,27 @@ __device__ __forceinline__ void warp_process_row(const Params& P, const Centroid
     }
 }
 
+template <int OP, int AUX, int R, bool VEC, bool FULL>
+__device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen,
+                                                 const RegTable<(OP == OP_NONUNIFORM && AUX <= 8 ? AUX : 0)>& rt, int64_t row,
+                                                 int lane) {
+    float v[4 * R], gv[4 * R];
+    warp_load_row<OP, AUX, R, VEC, FULL>(P, row, lane, v, gv);
+    warp_compute_row<OP, AUX, R, VEC, FULL>(P, cen, rt, row, lane, v, gv);
+}
+
+// Forward-only ops move 8-9 B/elt and, once the divisions were gone, were limited by the
+// number of loads in flight (2 x LDG.128 per lane); they keep the NEXT row's loads in flight
+// while the current row is reduced, quantized and stored (register double buffering).
+template <int OP, int AUX>
+constexpr bool kPrefetchNextRow = (OP != OP_UNIFORM) || (AUX == (int)BWD_OFF);
+
 template <int OP, int AUX, int R, bool VEC>
 __global__ void __launch_bounds__(kWarpCtaThreads) warp_rows_kernel(const __grid_constant__ Params P) {
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
     __shared__ float s_m[OP == OP_NONUNIFORM ? 256 : 1];
     Centroids cen{s_k, s_m, P.num_points};
-    RegTable<(OP == OP_NONUNIFORM ? AUX : 0)> rt;
+    RegTable<(OP == OP_NONUNIFORM && AUX <= 8 ? AUX : 0)> rt;
     if constexpr (OP == OP_NONUNIFORM) {
         centroid_setup(s_k, s_m, P.points, P.num_points);
         __syncthreads();
@@ -352,14 +372,31 @@ __global__ void __launch_bounds__(kWarpCtaThreads) warp_rows_kernel(const __grid
     }
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
-    const bool row_is_full = VEC && (P.geo.row_len == R * 128);
-    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < P.geo.rows; row += stride) {
-        const bool full = row_is_full && ((row + 1) * P.geo.row_len <= P.geo.n);
-        if (full)
-            warp_process_row<OP, AUX, R, VEC, VEC>(P, cen, rt, row, lane);  // FULL only exists for VEC
-        else
-            warp_process_row<OP, AUX, R, VEC, false>(P, cen, rt, row, lane);
+    int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    // rows [0, full_rows) are complete, 16-byte aligned rows of exactly R*128 elements
+    const int64_t full_rows = (VEC && P.geo.row_len == R * 128) ? (P.geo.n / P.geo.row_len) : 0;
+    if constexpr (VEC) {
+        if constexpr (kPrefetchNextRow<OP, AUX> && R <= 4) {
+            if (row < full_rows) {
+                float v[4 * R], gv[4 * R];
+                warp_load_row<OP, AUX, R, true, true>(P, row, lane, v, gv);
+                while (true) {
+                    const int64_t next = row + stride;
+                    const bool has_next = next < full_rows;
+                    float vn[4 * R], gn[4 * R];
+                    if (has_next) warp_load_row<OP, AUX, R, true, true>(P, next, lane, vn, gn);
+                    warp_compute_row<OP, AUX, R, true, true>(P, cen, rt, row, lane, v, gv);
+                    row = next;
+                    if (!has_next) break;
+#pragma unroll
+                    for (int i = 0; i < 4 * R; ++i) { v[i] = vn[i]; gv[i] = gn[i]; }
+                }
+            }
+        } else {
+            for (; row < full_rows; row += stride) warp_process_row<OP, AUX, R, true, true>(P, cen, rt, row, lane);
+        }
     }
+    for (; row < P.geo.rows; row += stride) warp_process_row<OP, AUX, R, VEC, false>(P, cen, rt, row, lane);
 }
 
 }  // namespace qd
