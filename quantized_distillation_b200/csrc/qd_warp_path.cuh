@@ -313,17 +313,32 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
     if constexpr (OP == OP_NONUNIFORM) {
         float qv[E];
         int li[E];
+        // x_hat = (x - beta) / alpha, bit-identical to div.rn.f32: hoisted-reciprocal sequence for the
+        // whole row, one warp vote, IEEE routine for the (rare) rows holding an element outside the
+        // sequence's proven domain (see RowDivider)
         const RowDivider div(rs.alpha);
+        const float thr = div.thr();
+        float xh[E];
+        bool unsafe = !div.ok;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            const float xh = div.exact(__fsub_rn(v[i], rs.beta));       // == to_unit(), bit for bit
+            const float a = __fsub_rn(v[i], rs.beta);
+            xh[i] = div.fast(a);
+            unsafe = unsafe || div.needs_exact(a, thr);
+        }
+        if (__any_sync(kFullMask, unsafe)) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) xh[i] = RowDivider::slow_div(__fsub_rn(v[i], rs.beta), rs.alpha);
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
             float kval;
             if constexpr (KR > 8) {
-                li[i] = smem_index<KR>(cen.k, cen.m, cen.K, xh, P.rule, kval);
+                li[i] = smem_index<KR>(cen.k, cen.m, cen.K, xh[i], P.rule, kval);
             } else if constexpr (KR > 0) {
-                li[i] = rt.index(xh, P.rule, cen.K, kval);
+                li[i] = rt.index(xh[i], P.rule, cen.K, kval);
             } else {
-                li[i] = centroid_index(cen, xh, P.rule);
+                li[i] = centroid_index(cen, xh[i], P.rule);
                 kval = cen.k[li[i]];
             }
             qv[i] = from_unit(kval, rs.alpha, rs.beta);

@@ -302,6 +302,29 @@ def test_nonuniform_vs_oracle(Q, bucket):
                 assert_same(qd.cpu().numpy(), q, f"{rule} q n={n} K={K} b={bucket}")
 
 
+def test_nonuniform_tiny_and_degenerate_rows(Q):
+    """Rows that push x_hat's division outside the hoisted-reciprocal domain: tiny non-zero
+    distances from the minimum, huge / tiny alpha, constant rows."""
+    pts = np.array([0.0, 1e-30, 0.5, 1.0], np.float32)
+    rows = [np.array([0.0, 1e-38, 1e-30, 1e-12, 0.5, 1.0, 3e-39, 1e-20] * 32, np.float32),
+            np.array([0.0, 3e38, 1e10, 1.0] * 64, np.float32),
+            np.array([1.0, 1.0 + 1e-7] * 128, np.float32),
+            np.full(256, -2.5, np.float32),
+            (np.arange(256) * 1e-42).astype(np.float32)]
+    x = np.concatenate(rows)
+    for rule in ("nearest", "midpoint"):
+        with np.errstate(all="ignore"):
+            q, idx, st = O.nonuniform_fwd(x, pts, 256, rule=rule)
+        if rule == "nearest":
+            qd, idxd, _ = Q.nonUniformQuantization(dev(x), dev(pts), bucket_size=256)
+        else:
+            f = Q.nonUniformQuantization_variable(bucket_size=256, pre_process_tensors=True, tensor=dev(x))
+            qd = f.forward(None, dev(pts))
+            idxd = f.savedForBackward["indices"].to(torch.int64)
+        assert_same(idxd.cpu().numpy(), idx, f"tiny {rule} idx")
+        assert_same(qd.cpu().numpy(), q, f"tiny {rule} q")
+
+
 @pytest.mark.parametrize("bucket", [None, 256, 100])
 def test_points_gradient_vs_oracle(Q, bucket):
     rng = np.random.default_rng(17)
