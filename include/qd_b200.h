@@ -142,7 +142,12 @@ typedef struct qd_plan qd_plan;
 int qd_plan_create(qd_plan** plan, int count, const float* const* src, float* const* dst, const int64_t* n,
                    const int32_t* levels, int64_t bucket);
 int qd_plan_destroy(qd_plan* plan);
+/* Optional shadow buffers (one per tensor, n[i] floats): when set, qd_plan_uniform_fwd with
+ * save != 0 also writes the untouched full-precision row there -- the reference's
+ * `model_state_dict = model.state_dict()` (conv_forward_model.py:286) for free in the same pass. */
+int qd_plan_set_shadow(qd_plan* plan, float* const* shadow);
 int qd_plan_uniform_fwd(const qd_plan* plan, qd_stream_t stream);
+int qd_plan_uniform_fwd_save(const qd_plan* plan, qd_stream_t stream);
 /* gout_i = bwd(src_i, grad_i) for every tensor, in place in grad. */
 int qd_plan_uniform_bwd(const qd_plan* plan, float* const* grad, int mode, qd_stream_t stream);
 

@@ -6,7 +6,9 @@ SURVEY.md section 3.1).  /root/reference does not exist on the GPU box, so this
 module restates that chain, op for op and pass for pass, with the same torch
 CPU kernels, so that ``bench.py --impl reference`` and the ``cpu_baseline`` leg
 time the same memory passes the reference makes on the host cores
-(``kind: "port"``).  It is also a second oracle, independent of the NumPy one,
+(``kind: "port"``).  The functions are device-agnostic like the reference's own code, so
+tools/plan_bench.py can also time "the reference's stock-torch op chain on the same
+B200" next to the fused kernels.  It is also a second oracle, independent of the NumPy one,
 and is pinned bit-for-bit against the golden vectors in
 tests/test_oracle_golden.py::test_torch_chain_matches_golden.
 
@@ -34,7 +36,7 @@ def _rows(t: torch.Tensor, bucket):
     n = t.numel()
     multiple, rest = divmod(n, bucket)
     if multiple != 0 and rest != 0:
-        t = torch.cat([t, torch.ones(bucket - rest) * t[-1]])
+        t = torch.cat([t, torch.ones(bucket - rest, device=t.device) * t[-1]])   # .cuda() in the reference (:84)
     return t.view(1, n) if multiple == 0 else t.view(-1, bucket)
 
 
@@ -84,22 +86,22 @@ def uniform_bwd_minmax(x: torch.Tensor, g: torch.Tensor, s: int, bucket: int):
     row_len = st.rows_shape[1]
     alpha = st.alpha.expand(rows, row_len).contiguous().view(-1)[0:n]
     beta = st.beta.expand(rows, row_len).contiguous().view(-1)[0:n]
-    adder = torch.arange(0, row_len * rows, row_len).view(-1, 1)
+    adder = torch.arange(0, row_len * rows, row_len, device=g.device).view(-1, 1)
     amax = (st.argmax + adder).view(-1)
     amin = (st.argmin + adder).view(-1)
     v = g.view(-1) * (qh - (saved.view(-1) - beta) / alpha)
     # M^T v of the reference (:380-400): per bucket r_b = sum_j v_j, +r_b at argmax', -r_b at argmin'
-    vp = torch.zeros(rows * row_len)
+    vp = torch.zeros(rows * row_len, device=g.device)
     vp[0:n] = v
     r = vp.view(rows, row_len).sum(dim=1)
-    corr = torch.zeros(n).index_add_(0, amax, r).index_add_(0, amin, -r)
+    corr = torch.zeros(n, device=g.device).index_add_(0, amax, r).index_add_(0, amin, -r)
     return (g.view(-1) + corr).view(g.size())
 
 
 def nonuniform_fwd(x: torch.Tensor, points: torch.Tensor, bucket, rule="nearest"):
     """quant_functions.py:243-290: scale on torch, index search on host numpy."""
     t, st = scale_down_(x.clone(), bucket)
-    v = t.view(-1).numpy()
+    v = t.view(-1).cpu().numpy()                           # device -> host like the reference (:255-258)
     k = points.cpu().numpy()
     if rule == "nearest":                                  # :267-273
         i = np.searchsorted(k, v, side="left").clip(max=k.size - 1)
@@ -108,8 +110,8 @@ def nonuniform_fwd(x: torch.Tensor, points: torch.Tensor, bucket, rule="nearest"
     else:                                                  # :531-573 closed form
         mid = k[:-1] + np.diff(k) / 2
         i = np.searchsorted(mid, v, side="right")
-    out = torch.from_numpy(k[i]).view(*st.rows_shape)
-    idx = torch.from_numpy(np.asarray(i)).long()
+    out = torch.from_numpy(k[i]).view(*st.rows_shape).to(x.device)   # host -> device (:282-284)
+    idx = torch.from_numpy(np.asarray(i)).long().to(x.device)
     q = inv_scale_down_(out, st)
     return q, idx.view(-1)[0:st.n].view(st.shape), st
 
@@ -119,7 +121,7 @@ def nonuniform_bwd_points(g: torch.Tensor, idx: torch.Tensor, st: ChainState, nu
     m = _rows(g.clone(), bucket)
     m = m * st.alpha.expand_as(m)
     m = m.view(-1)[0:g.numel()].view(g.size())
-    out = torch.zeros(num_points)
+    out = torch.zeros(num_points, device=g.device)
     for k in range(num_points):
         out[k] = torch.masked_select(m, idx == k).sum()
     return out

@@ -39,7 +39,9 @@ SIGNATURES = {
     "qd_index_histogram": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "qd_plan_create": (C.c_int, [C.POINTER(_p), _i32, _p, _p, _p, _p, _i64]),
     "qd_plan_destroy": (C.c_int, [_p]),
+    "qd_plan_set_shadow": (C.c_int, [_p, _p]),
     "qd_plan_uniform_fwd": (C.c_int, [_p, _p]),
+    "qd_plan_uniform_fwd_save": (C.c_int, [_p, _p]),
     "qd_plan_uniform_bwd": (C.c_int, [_p, _p, _i32, _p]),
     "qd_uniform_fwd_host": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32]),
     "qd_uniform_fwd_bwd_host": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32]),

@@ -143,8 +143,9 @@ class WeightQuantizer:
             torch._foreach_clamp_min_([p.data for p in self.params], -1.0)   # p.data.clamp_(-1, 1), reference :240-241
             torch._foreach_clamp_max_([p.data for p in self.params], 1.0)
         if save:
-            self.plan.save_master()
-        self.plan.quantize_()
+            self.plan.save_and_quantize_()          # shadow copy + in-place quantization, one launch
+        else:
+            self.plan.quantize_()
 
     def restore_weights_model(self):
         self.plan.restore_master()

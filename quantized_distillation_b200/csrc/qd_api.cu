@@ -460,6 +460,7 @@ struct qd_plan {
     int64_t total_rows = 0;
     int64_t max_row_len = 0;
     bool warp_path = true;
+    bool has_shadow = false;
     std::vector<PlanEntry> host;
     PlanEntry* dev = nullptr;
     float** dev_grads = nullptr;  // count pointers, refreshed per backward call
@@ -486,7 +487,7 @@ extern "C" int qd_plan_create(qd_plan** out, int count, const float* const* src,
             return fail(QD_ERR_INVALID_ARG, "bad tensor %d in plan (n=%lld levels=%d)", i, (long long)n[i], levels[i]);
         }
         PlanEntry& e = p->host[i];
-        e.src = src[i]; e.dst = dst[i]; e.n = n[i]; e.row_start = row; e.rows = g.rows; e.row_len = g.row_len;
+        e.src = src[i]; e.dst = dst[i]; e.save = nullptr; e.n = n[i]; e.row_start = row; e.rows = g.rows; e.row_len = g.row_len;
         e.S = (float)(levels[i] - 1);
         e.rS = 1.0f / e.S;
         e.lim = 0.5f - e.S * 0x1p-20f;
@@ -519,8 +520,19 @@ extern "C" int qd_plan_destroy(qd_plan* p) {
     return QD_OK;
 }
 
+extern "C" int qd_plan_set_shadow(qd_plan* p, float* const* shadow) {
+    if (p == nullptr || shadow == nullptr) return fail(QD_ERR_INVALID_ARG, "plan or shadow is NULL");
+    for (int i = 0; i < p->count; ++i) {
+        if (shadow[i] == nullptr) return fail(QD_ERR_INVALID_ARG, "shadow[%d] is NULL", i);
+        p->host[i].save = shadow[i];
+    }
+    QD_CUDA(cudaMemcpy(p->dev, p->host.data(), sizeof(PlanEntry) * p->count, cudaMemcpyHostToDevice));
+    p->has_shadow = true;
+    return QD_OK;
+}
+
 template <int BWD>
-static int plan_launch(const qd_plan* p, float* const* dev_grads, cudaStream_t s) {
+static int plan_launch(const qd_plan* p, float* const* dev_grads, cudaStream_t s, int with_save = 0) {
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
@@ -530,7 +542,7 @@ static int plan_launch(const qd_plan* p, float* const* dev_grads, cudaStream_t s
         auto kern = plan_rows_kernel<BWD, RR>;                                                    \
         int64_t cap = (int64_t)di->sms * resident_ctas(kern, kWarpCtaThreads, 0);                 \
         int grid = (int)(need < cap ? need : cap);                                                \
-        kern<<<grid, kWarpCtaThreads, 0, s>>>(p->dev, p->count, p->total_rows, dev_grads);        \
+        kern<<<grid, kWarpCtaThreads, 0, s>>>(p->dev, p->count, p->total_rows, dev_grads, with_save); \
     }
     if (p->max_row_len <= 256) QD_PLAN_LAUNCH(2)
     else if (p->max_row_len <= 512) QD_PLAN_LAUNCH(4)
@@ -551,6 +563,18 @@ extern "C" int qd_plan_uniform_fwd(const qd_plan* p, qd_stream_t stream) {
         if (rc) return rc;
     }
     return QD_OK;
+}
+
+extern "C" int qd_plan_uniform_fwd_save(const qd_plan* p, qd_stream_t stream) {
+    if (p == nullptr) return fail(QD_ERR_INVALID_ARG, "plan is NULL");
+    if (!p->has_shadow) return fail(QD_ERR_INVALID_ARG, "qd_plan_set_shadow has not been called");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->warp_path) return plan_launch<BWD_OFF>(p, nullptr, s, 1);
+    for (int i = 0; i < p->count; ++i) {  // long rows: copy, then the per-tensor block / grid path
+        const PlanEntry& e = p->host[i];
+        QD_CUDA(cudaMemcpyAsync(e.save, e.src, (size_t)e.n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return qd_plan_uniform_fwd(p, stream);
 }
 
 extern "C" int qd_plan_uniform_bwd(const qd_plan* p, float* const* grad, int mode, qd_stream_t stream) {

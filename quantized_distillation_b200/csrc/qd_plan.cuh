@@ -14,6 +14,7 @@ namespace qd {
 struct PlanEntry {
     const float* src;
     float* dst;
+    float* save;        // optional: full-precision copy of src written by the forward launch (shadow buffer)
     int64_t n;
     int64_t row_start;  // first global row of this tensor
     int64_t rows;
@@ -26,9 +27,26 @@ struct PlanEntry {
 
 constexpr int kPlanSmemEntries = 256;
 
+// forward of one plan row; with a shadow pointer the row is also written, untouched, to the
+// master copy (save + quantize in one pass: read 4, write 4 + 4 bytes per element)
+template <int R, bool VEC, bool FULL>
+__device__ __forceinline__ void plan_forward_row(const Params& P, float* save, int64_t row, int lane) {
+    float v[4 * R], gv[4 * R];
+    Centroids cen{nullptr, nullptr, 0};
+    RegTable<0> rt;
+    warp_load_row<OP_UNIFORM, BWD_OFF, R, VEC, FULL>(P, row, lane, v, gv);
+    if (save != nullptr) {
+        const int64_t base = row * P.geo.row_len;
+        const int len = FULL ? R * 128 : (int)min(P.geo.row_len, P.geo.n - base);
+        store_row<R, VEC, FULL>(save + base, len, lane, v);
+    }
+    warp_compute_row<OP_UNIFORM, BWD_OFF, R, VEC, FULL>(P, cen, rt, row, lane, v, gv);
+}
+
 template <int BWD, int R>
 __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEntry* __restrict__ entries, int count,
-                                                                   int64_t total_rows, float* const* __restrict__ grads) {
+                                                                   int64_t total_rows, float* const* __restrict__ grads,
+                                                                   int with_save) {
     __shared__ int64_t s_start[kPlanSmemEntries];
     const bool in_smem = count <= kPlanSmemEntries;
     if (in_smem) {
@@ -60,8 +78,17 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEn
         const int64_t row = grow - en.row_start;
         bool vec = en.vec != 0;
         if constexpr (BWD != BWD_OFF) vec = vec && ((reinterpret_cast<uintptr_t>(P.g) & 15) == 0);
-        if (vec) {
-            const bool full = (en.row_len == R * 128) && ((row + 1) * en.row_len <= en.n);
+        const bool full = (en.row_len == R * 128) && ((row + 1) * en.row_len <= en.n);
+        if constexpr (BWD == BWD_OFF) {
+            float* save = with_save ? en.save : nullptr;
+            if (vec && save != nullptr) vec = (reinterpret_cast<uintptr_t>(save) & 15) == 0;
+            if (vec) {
+                if (full) plan_forward_row<R, true, true>(P, save, row, lane);
+                else plan_forward_row<R, true, false>(P, save, row, lane);
+            } else {
+                plan_forward_row<R, false, false>(P, save, row, lane);
+            }
+        } else if (vec) {
             if (full) warp_process_row<OP_UNIFORM, BWD, R, true, true>(P, cen, rt, row, lane);
             else warp_process_row<OP_UNIFORM, BWD, R, true, false>(P, cen, rt, row, lane);
         } else {

@@ -429,6 +429,11 @@ def test_multi_tensor_plan_matches_per_tensor(Q):
         plan.restore_master()
         for p, m in zip(params, master):
             assert torch.equal(p, m)
+        originals = [p.clone() for p in params]
+        fused_master = plan.save_and_quantize_()          # one pass: shadow copy + in-place quantization
+        for p, r, m, o in zip(params, ref, fused_master, originals):
+            assert torch.equal(p, r) and torch.equal(m, o)
+        plan.restore_master()
         if bucket is not None:
             grads = [dev(rng.standard_normal(n).astype(np.float32)) for n in sizes]
             expect = []
