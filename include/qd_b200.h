@@ -134,6 +134,19 @@ int qd_centroid_index(const float* xhat, const float* points, int num_points, in
  * counts is a device int64[num_bins] the caller zeroes (it accumulates across tensors). */
 int qd_index_histogram(const uint8_t* idx_u8, int64_t n, int num_bins, int64_t* counts, qd_stream_t stream);
 
+/* ---- next row f2: packed integer codec (the compressed-model deliverable the reference only
+ * accounts for: helpers/functions.py:216-262).  bits in {1, 2, 4, 8}; code i of element e sits in
+ * byte e*bits/8 at bit offset (e*bits)%8 (little endian).  packed has ceil(n*bits/8) bytes. */
+int qd_pack_indices(const uint8_t* idx_u8, uint8_t* packed, int64_t n, int bits, qd_stream_t stream);
+/* q[n] rebuilt from packed uniform levels and the per-row (alpha, beta): bit-identical to the
+ * output of qd_uniform_fwd that produced the levels. */
+int qd_unpack_dequant_uniform(const uint8_t* packed, int bits, const float* alpha, const float* beta, float* q,
+                              int64_t n, int64_t bucket, int levels, qd_stream_t stream);
+/* same for centroid codes: q = points[code]*alpha + beta */
+int qd_unpack_dequant_nonuniform(const uint8_t* packed, int bits, const float* points, int num_points,
+                                 const float* alpha, const float* beta, float* q, int64_t n, int64_t bucket,
+                                 qd_stream_t stream);
+
 /* ---- next row f1: one launch over every parameter tensor of a model ------
  * (replaces the per-tensor loop of cnn_models/conv_forward_model.py:236-247).
  * A plan owns a device-side table of (src, dst, n, levels); pointers must stay

@@ -37,6 +37,9 @@ SIGNATURES = {
     "qd_nonuniform_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i64, _i64, _p, _sz, _p]),
     "qd_centroid_index": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i64, _p]),
     "qd_index_histogram": (C.c_int, [_p, _i64, _i32, _p, _p]),
+    "qd_pack_indices": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "qd_unpack_dequant_uniform": (C.c_int, [_p, _i32, _p, _p, _p, _i64, _i64, _i32, _p]),
+    "qd_unpack_dequant_nonuniform": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _p, _i64, _i64, _p]),
     "qd_plan_create": (C.c_int, [C.POINTER(_p), _i32, _p, _p, _p, _p, _i64]),
     "qd_plan_destroy": (C.c_int, [_p]),
     "qd_plan_set_shadow": (C.c_int, [_p, _p]),

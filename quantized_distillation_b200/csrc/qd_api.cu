@@ -453,6 +453,114 @@ extern "C" int qd_index_histogram(const uint8_t* idx_u8, int64_t n, int num_bins
     return QD_OK;
 }
 
+// ------------------------------------------------------------------ f2: packed codec
+// one thread = 8 consecutive codes in, `bits` bytes out
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ idx, uint8_t* __restrict__ packed, int64_t n,
+                                                  int bits) {
+    const int64_t groups = (n + 7) / 8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const unsigned mask = (1u << bits) - 1u;
+    for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += stride) {
+        unsigned long long word = 0;
+        const int64_t e0 = gidx * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned c = (e0 + j < n) ? (idx[e0 + j] & mask) : 0u;
+            word |= (unsigned long long)c << (j * bits);
+        }
+        const int64_t out_bytes = (n * bits + 7) / 8;
+        for (int b = 0; b < bits; ++b)
+            if (gidx * bits + b < out_bytes) packed[gidx * bits + b] = (uint8_t)(word >> (8 * b));
+    }
+}
+
+extern "C" int qd_pack_indices(const uint8_t* idx_u8, uint8_t* packed, int64_t n, int bits, qd_stream_t stream) {
+    if (idx_u8 == nullptr || packed == nullptr || n <= 0) return fail(QD_ERR_INVALID_ARG, "NULL argument or n <= 0");
+    if (bits != 1 && bits != 2 && bits != 4 && bits != 8) return fail(QD_ERR_INVALID_ARG, "bits must be 1, 2, 4 or 8");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    int64_t need = ((n + 7) / 8 + 255) / 256;
+    int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
+    pack_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx_u8, packed, n, bits);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+template <bool UNIFORM>
+__global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __restrict__ packed, int bits,
+                                                            const float* __restrict__ points, int K,
+                                                            const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                            float* __restrict__ q, Geometry geo, float S, float rS) {
+    __shared__ float s_pts[256];
+    if (!UNIFORM) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pts[i] = (i < K) ? points[i] : 0.f;
+        __syncthreads();
+    }
+    const int64_t groups = (geo.n + 7) / 8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const unsigned mask = (1u << bits) - 1u;
+    const int64_t in_bytes = (geo.n * bits + 7) / 8;
+    for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += stride) {
+        unsigned long long word = 0;
+        for (int b = 0; b < bits; ++b)
+            if (gidx * bits + b < in_bytes) word |= (unsigned long long)packed[gidx * bits + b] << (8 * b);
+        const int64_t e0 = gidx * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t e = e0 + j;
+            if (e >= geo.n) break;
+            const unsigned c = (unsigned)(word >> (j * bits)) & mask;
+            const int64_t row = e / geo.row_len;
+            float unit;
+            if (UNIFORM) unit = (S <= 255.0f) ? small_level_to_unit((float)c, S, rS) : level_to_unit((float)c, S);
+            else unit = s_pts[c];
+            q[e] = from_unit(unit, alpha[row], beta[row]);
+        }
+    }
+}
+
+static int unpack_common(const uint8_t* packed, int bits, const float* alpha, const float* beta, float* q, int64_t n,
+                         int64_t bucket, Geometry* geo, int* grid) {
+    if (packed == nullptr || alpha == nullptr || beta == nullptr || q == nullptr) return fail(QD_ERR_INVALID_ARG, "NULL argument");
+    if (bits != 1 && bits != 2 && bits != 4 && bits != 8) return fail(QD_ERR_INVALID_ARG, "bits must be 1, 2, 4 or 8");
+    if (geometry_of(n, bucket, geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    int64_t need = ((n + 7) / 8 + 255) / 256;
+    *grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
+    return QD_OK;
+}
+
+extern "C" int qd_unpack_dequant_uniform(const uint8_t* packed, int bits, const float* alpha, const float* beta, float* q,
+                                         int64_t n, int64_t bucket, int levels, qd_stream_t stream) {
+    Geometry geo;
+    int grid = 0;
+    if (levels < 2 || levels > (1 << bits)) return fail(QD_ERR_INVALID_ARG, "levels must be in [2, 2^bits]");
+    int rc = unpack_common(packed, bits, alpha, beta, q, n, bucket, &geo, &grid);
+    if (rc) return rc;
+    const float S = (float)(levels - 1);
+    unpack_dequant_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, bits, nullptr, 0, alpha, beta,
+                                                                                        q, geo, S, 1.0f / S);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_unpack_dequant_nonuniform(const uint8_t* packed, int bits, const float* points, int num_points,
+                                            const float* alpha, const float* beta, float* q, int64_t n, int64_t bucket,
+                                            qd_stream_t stream) {
+    Geometry geo;
+    int grid = 0;
+    if (points == nullptr || num_points < 1 || num_points > (1 << bits)) return fail(QD_ERR_INVALID_ARG, "num_points must be in [1, 2^bits]");
+    int rc = unpack_common(packed, bits, alpha, beta, q, n, bucket, &geo, &grid);
+    if (rc) return rc;
+    unpack_dequant_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, bits, points, num_points,
+                                                                                         alpha, beta, q, geo, 0.f, 0.f);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
 // ------------------------------------------------------------------ plans (f1)
 struct qd_plan {
     int count = 0;

@@ -517,3 +517,41 @@ def test_full_size_properties_64M(Q):
     changed = np.nonzero(go.cpu().numpy() != gd.cpu().numpy())[0]
     assert changed.size <= 2 * (n // b) and np.array_equal(changed, np.nonzero(ref != gd.cpu().numpy())[0])
     assert diff.max() <= 1e-4, diff.max()
+
+
+def test_packed_codec_round_trip(Q):
+    """encode -> (bit-packed codes, alpha, beta) -> decode reproduces the fused fake-quant output bit for bit."""
+    from quantized_distillation_b200 import codec
+    rng = np.random.default_rng(47)
+    for n in (1, 7, 8, 9, 255, 256, 257, 5000, 300001):
+        x = dev((rng.standard_normal(n) * 0.05).astype(np.float32))
+        for s, bucket in ((2, 256), (4, 256), (16, 256), (256, 256), (16, None), (3, 100), (200, 4096)):
+            pt = codec.encode_uniform(x, s, bucket)
+            assert pt.bits == codec.bits_for(s) and pt.packed.numel() == (n * pt.bits + 7) // 8
+            q, _ = Q.uniformQuantization(x, s, bucket_size=bucket)
+            assert torch.equal(codec.decode(pt), q), (n, s, bucket)
+        for K, rule in ((4, "nearest"), (16, "midpoint"), (3, "nearest")):
+            pts = np.sort(rng.random(K)).astype(np.float32)
+            pt = codec.encode_nonuniform(x, pts, 256, rule=rule)
+            if rule == "nearest":
+                qn, _, _ = Q.nonUniformQuantization(x, dev(pts), bucket_size=256)
+            else:
+                qn = Q.nonUniformQuantization_variable(bucket_size=256, pre_process_tensors=True, tensor=x).forward(None, dev(pts))
+            assert torch.equal(codec.decode(pt), qn), (n, K, rule)
+    big = codec.encode_uniform(dev(rng.standard_normal(1 << 20).astype(np.float32)), 16, 256)
+    assert abs(big.nbytes / (4 << 20) - 1 / codec.get_size_reduction(4, 256)) < 1e-6      # 4-bit + 8 B per 256 weights
+    assert codec.get_size_reduction(4, None) == 8
+
+
+def test_size_accounting_matches_reference_formula(Q):
+    from quantized_distillation_b200 import codec
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(64, 300), torch.nn.ReLU(), torch.nn.Linear(300, 10)).cuda()
+    fun = lambda t: Q.uniformQuantization(t, 16, bucket_size=256)  # noqa: E731
+    mb = codec.get_size_quantized_model(model, 4, fun, bucket_size=256, quantizeFirstLastLayer=False)
+    params = list(model.parameters())
+    mbl = Q.help_functions.get_huffman_encoding_mean_bit_length(iter(params[1:-1]), fun, "uniform", s=16)
+    count_q = sum(p.numel() for p in params[1:-1])
+    count_u = params[0].numel() + params[-1].numel()
+    assert abs(mb - (count_u * 4 + mbl * count_q / 8 + count_q / 256 * 8) / 1e6) < 1e-12
+    assert codec.get_size_quantized_model(model, None, fun) == sum(p.numel() for p in params) * 4 / 1e6
