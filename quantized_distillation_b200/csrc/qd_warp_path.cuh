@@ -374,8 +374,16 @@ __device__ __forceinline__ void warp_process_row(const Params& P, const Centroid
 template <int OP, int AUX>
 constexpr bool kPrefetchNextRow = (OP != OP_UNIFORM) || (AUX == (int)BWD_OFF);
 
+// minimum resident CTAs per SM the register allocator must allow: 256-element rows (every
+// experiment of the reference) are tuned for 4 x 8 warps per SM (<= 64 registers); the fused
+// min/max kernel gained 3-5 % from the extra occupancy (profiles/sweep_r1_full.md)
+// (measured per kernel: the forward-only and min/max kernels gain, STE / truncated / non-uniform
+// are better with ptxas's own choice, 0 = unconstrained)
+template <int OP, int AUX, int R>
+constexpr int kMinCtas = (OP == OP_UNIFORM && R == 2 && (AUX == (int)BWD_OFF || AUX == (int)BWD_MINMAX)) ? 4 : 0;
+
 template <int OP, int AUX, int R, bool VEC>
-__global__ void __launch_bounds__(kWarpCtaThreads) warp_rows_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(kWarpCtaThreads, kMinCtas<OP, AUX, R>) warp_rows_kernel(const __grid_constant__ Params P) {
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
     __shared__ float s_m[OP == OP_NONUNIFORM ? 256 : 1];
     Centroids cen{s_k, s_m, P.num_points};
