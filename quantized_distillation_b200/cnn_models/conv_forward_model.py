@@ -307,12 +307,41 @@ def train_model_quantized(model, train_loader, test_loader, numBits=8, bucket_si
 # ------------------------------------------------------------------------------------------
 # differentiable quantization
 # ------------------------------------------------------------------------------------------
+def _capture_point_graphs(quantize_all, point_gradients, device):
+    """Captures the two per-step launch sequences of the differentiable-quantization loop.
+    Returns (forward_graph, backward_graph, gradient tensors) or False when capture fails."""
+    try:
+        torch.cuda.synchronize(device)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):                       # warm the capture stream's workspace / caches
+            quantize_all()
+            point_gradients()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        g_fwd, g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fwd):
+            quantize_all()
+        with torch.cuda.graph(g_bwd):
+            grads = point_gradients()
+        return g_fwd, g_bwd, grads
+    except Exception as e:                                   # pragma: no cover - depends on driver / torch build
+        import warnings
+        warnings.warn(f"CUDA graph capture of the quantization step failed, running eagerly: {e}")
+        try:
+            torch.cuda.synchronize(device)
+        except Exception:
+            pass
+        return False
+
+
+
 def optimize_quantization_points(modelToQuantize, train_loader, test_loader, initial_learning_rate=1e-5,
                                  initial_momentum=0.9, epochs_to_train=30, print_every=500, use_nesterov=True,
                                  learning_rate_style="generic", numPointsPerTensor=16, assignBitsAutomatically=False,
                                  bucket_size=None, use_distillation_loss=True, initialize_method="quantiles",
                                  quantize_first_and_last_layer=True, *, max_steps=None, verbose=True, evaluate=True,
-                                 step_hook=None):
+                                 step_hook=None, use_cuda_graphs=True):
     """Learn the quantization points of every tensor by SGD on the loss of the
     quantized network, the unquantized network acting as teacher (reference
     :395-592).  Returns ``(quantizedModel.state_dict(), pointsPerTensor, informationDict)``."""
@@ -371,6 +400,19 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
         max_element=False, subtract_mean=False, modify_in_place=False, bucket_size=bucket_size,
         pre_process_tensors=True, tensor=p.data) for p in q_selected]         # :501-511
 
+    def quantize_all():                                                       # :525-532
+        for fun, p_q, pts in zip(quantizationFunctions, q_selected, pointsPerTensor):
+            fun.forward(None, pts.data, out=p_q.data)
+
+    def point_gradients():                                                    # :539-545
+        return [fun.backward(p_q.grad.data)[1] for fun, p_q in zip(quantizationFunctions, q_selected)]
+
+    # The per-step quantization work is 3 small launches per tensor (22-60 tensors): launch bound.
+    # After two eager steps (lazy initialisation done, every .grad allocated) the forward and the
+    # backward sequences are each captured into a CUDA graph and replayed with one call per step.
+    graphs = None
+    graph_after = 2 if (use_cuda_graphs and device.type == "cuda") else None
+
     total_steps, epoch, stop = 0, 0, False
     for epoch in range(epochs_to_train):
         quantizedModel.train()
@@ -378,16 +420,28 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
         for idx_minibatch, data in enumerate(train_loader, start=1):
             quantizedModel.zero_grad(set_to_none=False)
             optimizer.zero_grad(set_to_none=False)
-            for fun, p_q, pts in zip(quantizationFunctions, q_selected, pointsPerTensor):   # :525-532
-                fun.forward(None, pts.data, out=p_q.data)
+            if graphs is None and graph_after is not None and total_steps >= graph_after:
+                graphs = _capture_point_graphs(quantize_all, point_gradients, device)
+                if graphs is False:
+                    graph_after = None                                        # capture unavailable: stay eager
+                    graphs = None
+            if graphs:
+                graphs[0].replay()
+            else:
+                quantize_all()
             loss = cnn_hf.forward_and_backward(quantizedModel, data, idx_minibatch, epoch,
                                                use_distillation_loss=use_distillation_loss,
                                                teacher_model=modelToQuantize, return_tensor=True)
-            for fun, p_q, pts in zip(quantizationFunctions, q_selected, pointsPerTensor):   # :539-545
-                pts.grad.data = fun.backward(p_q.grad.data)[1]
+            if graphs:
+                graphs[1].replay()
+                grads = graphs[2]
+            else:
+                grads = point_gradients()
+            for pts, gp in zip(pointsPerTensor, grads):
+                pts.grad.data = gp
             optimizer.step()
-            for pts in pointsPerTensor:                                       # :550-551
-                pts.data = torch.sort(pts.data)[0]
+            for pts in pointsPerTensor:                                       # :550-551, in place: the graphs hold pts' address
+                pts.data.copy_(torch.sort(pts.data)[0])
             running += loss
             total_steps += 1
             if step_hook is not None:

@@ -165,3 +165,24 @@ def test_wide_resnet_quantized_step(env):
     assert info["numStepsTrained"] == 3
     params = list(model.parameters())
     assert distinct_per_bucket(params[5], 256) <= 4
+
+
+def test_diffquant_cuda_graph_path_matches_eager(env):
+    """The CUDA-graph replay of the per-step quantization launches gives the same centroids as eager launches."""
+    Q, cfm, hf = env
+    torch.backends.cudnn.deterministic = True
+    results = []
+    for use_graphs in (False, True):
+        torch.manual_seed(11)
+        model = make_student(cfm)
+        data = hf.synthetic_cifar_loader(6, 25, seed=9)
+        state, points, info = cfm.optimize_quantization_points(
+            model, data, data, initial_learning_rate=1e-3, epochs_to_train=1, print_every=3, numPointsPerTensor=4,
+            bucket_size=256, use_distillation_loss=True, initialize_method="quantiles", verbose=False, evaluate=False,
+            use_cuda_graphs=use_graphs)
+        assert info["numStepsTrained"] == 6
+        results.append([p.detach().clone() for p in points])
+    torch.backends.cudnn.deterministic = False
+    for a, b in zip(*results):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (a, b)
+    assert any(not torch.equal(a, b0) for a, b0 in zip(results[0], [torch.zeros_like(x) for x in results[0]]))
