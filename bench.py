@@ -207,7 +207,7 @@ def workload_config(n_gpus):
 
 
 # ----------------------------------------------------------------------------- training legs
-def run_train_leg(kind, world, rank, dev, steps, warmup):
+def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False):
     """CIFAR10-shaped quantized distillation steps/s (BASELINE configs 2-4), synthetic data,
     random-init weights.  Every step copies its batch from pinned host memory and reads the
     loss back (print_every=1), so the number is end to end.  DDP when world > 1."""
@@ -255,7 +255,7 @@ def run_train_leg(kind, world, rank, dev, steps, warmup):
         model = D.wrap_ddp(student, dev)
         cfm.train_model_quantized(model, data, data, numBits=bits, bucket_size=256, use_distillation_loss=True,
                                   teacher_model=teacher, epochs_to_train=1, print_every=1, verbose=False, evaluate=False,
-                                  max_steps=total, step_hook=hook, **kw)
+                                  max_steps=total, step_hook=hook, cuda_graph_step=graph, **kw)
         label = f"{bits}-bit quantized distillation, bucket 256 (BASELINE config {2 if kind == 'student' else 3})"
     torch.cuda.synchronize(dev)
     ms = ev["t0"].elapsed_time(ev["t1"]) / steps
@@ -416,6 +416,12 @@ def main():
                                "host_cpus_visible": os.cpu_count(), "host_cpus_usable": usable_cpus()}
     if args.train != "none":
         out["train"] = run_train_leg(args.train, world, rank, dev, args.train_steps, 8)
+        if world == 1 and args.train in ("student", "wrn"):
+            g = run_train_leg(args.train, world, rank, dev, args.train_steps, 8, graph=True)
+            out["train"]["cuda_graph_step"] = {"steps_per_s": g["steps_per_s"], "ms_per_step": g["ms_per_step"],
+                                               "note": "same step, same kernels, captured once in a CUDA graph and replayed "
+                                                       "(train_model(cuda_graph_step=True)); batch H2D copy and loss read-back "
+                                                       "still happen every step"}
         if rank == 0 and world == 1 and not args.no_cpu and args.train == "student":
             sizes = [5000, 10, 5625, 75, 93750, 50, 62500, 50, 31250, 25, 800000, 500] + [75, 75, 50, 50, 50, 50, 25, 25, 500, 500]
             out["train"]["cpu_reference_quantize_ms_per_step"] = round(cpu_model_quant_ms(sizes, 16, 256), 3)

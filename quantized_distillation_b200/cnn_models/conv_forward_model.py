@@ -105,6 +105,42 @@ class ConvolForwardNet(nn.Module):
 # ------------------------------------------------------------------------------------------
 # quantized distillation
 # ------------------------------------------------------------------------------------------
+class _GraphedStep:
+    """One whole training step captured in a CUDA graph: static input buffers, one replay per step."""
+
+    def __init__(self, step_fn, example_batch, device, stream, optimizer):
+        self.ok = False
+        try:
+            x, y = example_batch
+            self.x = torch.empty(x.shape, dtype=x.dtype, device=device)
+            self.y = torch.empty(y.shape, dtype=y.dtype, device=device)
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y, non_blocking=True)
+            torch.cuda.synchronize(device)
+            optimizer.zero_grad(set_to_none=True)            # gradients are re-created inside the graph's pool
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=stream):
+                self.loss, self.asked, self.total = step_fn((self.x, self.y))
+            self.ok = True
+        except Exception as e:                               # pragma: no cover - depends on driver / torch build
+            import warnings
+            warnings.warn(f"CUDA graph capture of the training step failed, running eagerly: {e}")
+            try:
+                torch.cuda.synchronize(device)
+            except Exception:
+                pass
+
+    def matches(self, batch):
+        return batch[0].shape == self.x.shape and batch[1].shape == self.y.shape
+
+    def run(self, batch):
+        self.x.copy_(batch[0], non_blocking=True)
+        self.y.copy_(batch[1], non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.asked, self.total
+
+
+
 def _selected_parameters(model, quantize_first_and_last_layer):
     params = list(model.parameters())
     if quantize_first_and_last_layer is False:
@@ -180,10 +216,17 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
                 backprop_quantization_style="none", estimate_quant_grad_every=1, add_gradient_noise=False,
                 ask_teacher_strategy=("always", None), quantize_first_and_last_layer=True,
                 mix_with_differentiable_quantization=False, *, max_steps=None, verbose=True, evaluate=True,
-                step_hook=None):
+                step_hook=None, cuda_graph_step=False):
     """SGD training with optional distillation loss and optional per-step weight
     quantization (reference :165-393; same positional/keyword arguments, the
-    keyword-only ones after ``*`` are additions for benchmarking)."""
+    keyword-only ones after ``*`` are additions).
+
+    ``cuda_graph_step=True`` (single process, ``ask_teacher_strategy`` 'always',
+    ``estimate_quant_grad_every`` 1): after three eager steps the whole step --
+    save+quantize, student/teacher forward, backward, restore, gradient fix-up,
+    SGD update -- is captured once in a CUDA graph and replayed; each step then
+    costs one H2D copy of the batch and one graph launch.  Same arithmetic, same
+    kernels; the graph is re-captured when the learning rate changes."""
     if use_distillation_loss is True and teacher_model is None:
         raise ValueError("To compute distillation loss you have to pass the teacher model")
     if teacher_model is not None:
@@ -208,36 +251,61 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
     total_steps = 0
     stop = False
     epoch = start_epoch
+    device = cnn_hf._device_of(model)
+    state = {"since": steps_since_estimate}
+
+    def one_step(data, idx_minibatch=1, epoch=0):
+        """One training step of the reference loop (:280-322) on one batch."""
+        quantize_now = quantizer is not None and state["since"] >= estimate_quant_grad_every
+        if quantize_now:
+            quantizer.quantize_weights_model()                            # :286-287
+        model.zero_grad(set_to_none=False)
+        loss, c_teach, c_total = cnn_hf.forward_and_backward(
+            model, data, idx_minibatch, epoch, use_distillation_loss=use_distillation_loss, teacher_model=teacher_model,
+            ask_teacher_strategy=ask_teacher_strategy, return_more_info=True, return_tensor=True)
+        if quantize_now:
+            quantizer.restore_weights_model()                             # :302
+        if add_gradient_noise and not quantizeWeights:
+            cnn_hf.add_gradient_noise(model, idx_minibatch, epoch, batches_per_epoch)
+        if grad_clipping_threshold is not False:
+            for p in model.parameters():
+                if p.grad is not None:
+                    p.grad.clamp_(-grad_clipping_threshold, grad_clipping_threshold)
+        if quantize_now:
+            quantizer.backward_quant_weights_model()                      # :315
+        optimizer.step()
+        if state["since"] >= estimate_quant_grad_every:
+            state["since"] = 0
+        state["since"] += 1
+        return loss, c_teach, c_total
+
+    strategy_name = (ask_teacher_strategy[0] if isinstance(ask_teacher_strategy, tuple) else ask_teacher_strategy).lower()
+    graph_ok = bool(cuda_graph_step and device.type == "cuda" and estimate_quant_grad_every == 1 and not add_gradient_noise
+                    and strategy_name == "always"
+                    and not (torch.distributed.is_available() and torch.distributed.is_initialized()
+                             and torch.distributed.get_world_size() > 1))
+    side_stream = torch.cuda.Stream(device) if graph_ok else None
+    graphed = None
     try:
         for epoch in range(start_epoch, epochs_to_train + start_epoch):
             model.train()
             running = torch.zeros((), device=cnn_hf._device_of(model))
             asked, seen = 0, 0
             for idx_minibatch, data in enumerate(train_loader, start=1):
-                quantize_now = quantizer is not None and steps_since_estimate >= estimate_quant_grad_every
-                if quantize_now:
-                    quantizer.quantize_weights_model()                    # :286-287
-                model.zero_grad(set_to_none=False)
-                loss, c_teach, c_total = cnn_hf.forward_and_backward(
-                    model, data, idx_minibatch, epoch, use_distillation_loss=use_distillation_loss,
-                    teacher_model=teacher_model, ask_teacher_strategy=ask_teacher_strategy, return_more_info=True,
-                    return_tensor=True)
+                if graph_ok and graphed is None and total_steps >= 3:
+                    graphed = _GraphedStep(one_step, data, device, side_stream, optimizer)
+                    if not graphed.ok:
+                        graph_ok, graphed = False, None
+                if graphed is not None and graphed.matches(data):
+                    loss, c_teach, c_total = graphed.run(data)
+                elif graph_ok:
+                    with torch.cuda.stream(side_stream):           # warm-up steps run where the capture will
+                        loss, c_teach, c_total = one_step(data, idx_minibatch, epoch)
+                    torch.cuda.current_stream(device).wait_stream(side_stream)
+                else:
+                    loss, c_teach, c_total = one_step(data, idx_minibatch, epoch)
                 asked += c_teach
                 seen += c_total
-                if quantize_now:
-                    quantizer.restore_weights_model()                     # :302
-                if add_gradient_noise and not quantizeWeights:
-                    cnn_hf.add_gradient_noise(model, idx_minibatch, epoch, batches_per_epoch)
-                if grad_clipping_threshold is not False:
-                    for p in model.parameters():
-                        if p.grad is not None:
-                            p.grad.clamp_(-grad_clipping_threshold, grad_clipping_threshold)
-                if quantize_now:
-                    quantizer.backward_quant_weights_model()              # :315
-                optimizer.step()
-                if steps_since_estimate >= estimate_quant_grad_every:
-                    steps_since_estimate = 0
-                steps_since_estimate += 1
                 running += loss
                 total_steps += 1
                 if step_hook is not None:
@@ -279,6 +347,8 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
             if stop_training is True:
                 break
             for group in optimizer.param_groups:
+                if group["lr"] != new_learning_rate:
+                    graphed = None                                         # the captured SGD update holds the old rate
                 group["lr"] = new_learning_rate
     except KeyboardInterrupt:
         informationDict["errorFlag"] = False

@@ -640,7 +640,10 @@ extern "C" int qd_plan_set_shadow(qd_plan* p, float* const* shadow) {
 }
 
 template <int BWD>
-static int plan_launch(const qd_plan* p, float* const* dev_grads, cudaStream_t s, int with_save = 0) {
+static int plan_launch(const qd_plan* p, float* const* dev_grads, cudaStream_t s, int with_save = 0,
+                       const GradTable* gtab = nullptr) {
+    static const GradTable kEmpty = {};
+    const GradTable& gt = gtab ? *gtab : kEmpty;
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
@@ -650,7 +653,7 @@ static int plan_launch(const qd_plan* p, float* const* dev_grads, cudaStream_t s
         auto kern = plan_rows_kernel<BWD, RR>;                                                    \
         int64_t cap = (int64_t)di->sms * resident_ctas(kern, kWarpCtaThreads, 0);                 \
         int grid = (int)(need < cap ? need : cap);                                                \
-        kern<<<grid, kWarpCtaThreads, 0, s>>>(p->dev, p->count, p->total_rows, dev_grads, with_save); \
+        kern<<<grid, kWarpCtaThreads, 0, s>>>(p->dev, p->count, p->total_rows, dev_grads, with_save, gt); \
     }
     if (p->max_row_len <= 256) QD_PLAN_LAUNCH(2)
     else if (p->max_row_len <= 512) QD_PLAN_LAUNCH(4)
@@ -698,12 +701,20 @@ extern "C" int qd_plan_uniform_bwd(const qd_plan* p, float* const* grad, int mod
         }
         return QD_OK;
     }
+    if (mode == QD_BWD_MINMAX && p->bucket == 0)
+        return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
+    if (mode != QD_BWD_TRUNCATED && mode != QD_BWD_MINMAX) return fail(QD_ERR_INVALID_ARG, "unknown backward mode %d", mode);
+    for (int i = 0; i < p->count; ++i)
+        if (grad[i] == nullptr) return fail(QD_ERR_INVALID_ARG, "grad[%d] is NULL", i);
+    if (p->count <= kPlanGradsByValue) {  // pointers ride in the launch parameters (graph-capturable)
+        GradTable gt = {};
+        for (int i = 0; i < p->count; ++i) gt.g[i] = grad[i];
+        return mode == QD_BWD_TRUNCATED ? plan_launch<BWD_TRUNC>(p, nullptr, s, 0, &gt)
+                                        : plan_launch<BWD_MINMAX>(p, nullptr, s, 0, &gt);
+    }
     QD_CUDA(cudaMemcpyAsync(p->dev_grads, grad, sizeof(float*) * p->count, cudaMemcpyHostToDevice, s));
     if (mode == QD_BWD_TRUNCATED) return plan_launch<BWD_TRUNC>(p, p->dev_grads, s);
-    if (mode == QD_BWD_MINMAX) {
-        if (p->bucket == 0) return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
-        return plan_launch<BWD_MINMAX>(p, p->dev_grads, s);
-    }
+    if (mode == QD_BWD_MINMAX) return plan_launch<BWD_MINMAX>(p, p->dev_grads, s);
     return fail(QD_ERR_INVALID_ARG, "unknown backward mode %d", mode);
 }
 

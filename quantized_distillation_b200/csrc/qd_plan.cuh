@@ -27,6 +27,14 @@ struct PlanEntry {
 
 constexpr int kPlanSmemEntries = 256;
 
+// Gradient pointers of the backward launch travel BY VALUE in the kernel parameters (up to 256
+// tensors = 2 KB): no host->device table copy per step, and the launch can be captured in a
+// CUDA graph (a captured memcpy from a temporary host array could not).
+constexpr int kPlanGradsByValue = 256;
+struct GradTable {
+    float* g[kPlanGradsByValue];
+};
+
 // forward of one plan row; with a shadow pointer the row is also written, untouched, to the
 // master copy (save + quantize in one pass: read 4, write 4 + 4 bytes per element)
 template <int R, bool VEC, bool FULL>
@@ -46,7 +54,7 @@ __device__ __forceinline__ void plan_forward_row(const Params& P, float* save, i
 template <int BWD, int R>
 __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEntry* __restrict__ entries, int count,
                                                                    int64_t total_rows, float* const* __restrict__ grads,
-                                                                   int with_save) {
+                                                                   int with_save, const __grid_constant__ GradTable gtab) {
     __shared__ int64_t s_start[kPlanSmemEntries];
     const bool in_smem = count <= kPlanSmemEntries;
     if (in_smem) {
@@ -68,8 +76,10 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEn
         Params P;
         P.x = en.src;
         P.q = (BWD == BWD_OFF) ? en.dst : nullptr;
-        P.g = (BWD == BWD_OFF) ? nullptr : grads[lo];
-        P.gout = (BWD == BWD_OFF) ? nullptr : grads[lo];
+        float* gptr = nullptr;
+        if constexpr (BWD != BWD_OFF) gptr = (grads != nullptr) ? grads[lo] : gtab.g[lo];
+        P.g = gptr;
+        P.gout = gptr;
         P.xhat = nullptr; P.idx8 = nullptr; P.idx64 = nullptr;
         P.alpha = nullptr; P.beta = nullptr; P.argmin = nullptr; P.argmax = nullptr;
         P.mean = nullptr; P.max_element = 0.f; P.points = nullptr; P.num_points = 0; P.rule = 0;

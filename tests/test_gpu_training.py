@@ -186,3 +186,24 @@ def test_diffquant_cuda_graph_path_matches_eager(env):
     for a, b in zip(*results):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (a, b)
     assert any(not torch.equal(a, b0) for a, b0 in zip(results[0], [torch.zeros_like(x) for x in results[0]]))
+
+
+@pytest.mark.parametrize("style", ["none", "complicated"])
+def test_whole_step_cuda_graph_matches_eager(env, style):
+    """cuda_graph_step=True replays exactly the eager step: same weights after 8 steps (up to cuDNN float noise)."""
+    Q, cfm, hf = env
+    torch.backends.cudnn.deterministic = True
+    finals = []
+    for graph in (False, True):
+        torch.manual_seed(21)
+        student = make_student(cfm)
+        teacher = make_student(cfm).eval()
+        data = hf.synthetic_cifar_loader(8, 25, seed=4)
+        model, info = cfm.train_model_quantized(student, data, data, numBits=4, bucket_size=256, use_distillation_loss=True,
+                                                teacher_model=teacher, epochs_to_train=1, print_every=4, verbose=False,
+                                                evaluate=False, backprop_quantization_style=style, cuda_graph_step=graph)
+        assert info["numStepsTrained"] == 8
+        finals.append([p.detach().clone() for p in model.parameters()])
+    torch.backends.cudnn.deterministic = False
+    for a, b in zip(*finals):
+        assert (a != b).float().mean() < 0.02, "more than a few level flips between graph and eager training"
