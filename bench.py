@@ -249,7 +249,7 @@ def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False):
         cfm.optimize_quantization_points(student, data, data, initial_learning_rate=1e-5, epochs_to_train=1, print_every=1,
                                          numPointsPerTensor=4, bucket_size=256, use_distillation_loss=True,
                                          initialize_method="quantiles", verbose=False, evaluate=False, max_steps=total,
-                                         step_hook=hook)
+                                         step_hook=hook, cuda_graph_step=graph)
         label = "differentiable quantization, 4 centroids per tensor, bucket 256 (BASELINE config 4)"
     else:
         model = D.wrap_ddp(student, dev)
@@ -416,7 +416,7 @@ def main():
                                "host_cpus_visible": os.cpu_count(), "host_cpus_usable": usable_cpus()}
     if args.train != "none":
         out["train"] = run_train_leg(args.train, world, rank, dev, args.train_steps, 8)
-        if world == 1 and args.train in ("student", "wrn"):
+        if world == 1:
             g = run_train_leg(args.train, world, rank, dev, args.train_steps, 8, graph=True)
             out["train"]["cuda_graph_step"] = {"steps_per_s": g["steps_per_s"], "ms_per_step": g["ms_per_step"],
                                                "note": "same step, same kernels, captured once in a CUDA graph and replayed "

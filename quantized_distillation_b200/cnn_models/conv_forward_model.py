@@ -411,7 +411,7 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
                                  learning_rate_style="generic", numPointsPerTensor=16, assignBitsAutomatically=False,
                                  bucket_size=None, use_distillation_loss=True, initialize_method="quantiles",
                                  quantize_first_and_last_layer=True, *, max_steps=None, verbose=True, evaluate=True,
-                                 step_hook=None, use_cuda_graphs=True):
+                                 step_hook=None, use_cuda_graphs=True, cuda_graph_step=False):
     """Learn the quantization points of every tensor by SGD on the loss of the
     quantized network, the unquantized network acting as teacher (reference
     :395-592).  Returns ``(quantizedModel.state_dict(), pointsPerTensor, informationDict)``."""
@@ -481,37 +481,58 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
     # After two eager steps (lazy initialisation done, every .grad allocated) the forward and the
     # backward sequences are each captured into a CUDA graph and replayed with one call per step.
     graphs = None
-    graph_after = 2 if (use_cuda_graphs and device.type == "cuda") else None
+    graph_after = 2 if (use_cuda_graphs and device.type == "cuda" and not cuda_graph_step) else None
+
+    def one_step(data, idx_minibatch=1, epoch=0):
+        """One step of the reference loop (:518-551)."""
+        nonlocal graphs, graph_after
+        quantizedModel.zero_grad(set_to_none=False)
+        optimizer.zero_grad(set_to_none=False)
+        if graphs is None and graph_after is not None and total_steps >= graph_after:
+            graphs = _capture_point_graphs(quantize_all, point_gradients, device)
+            if graphs is False:
+                graph_after, graphs = None, None                          # capture unavailable: stay eager
+        if graphs:
+            graphs[0].replay()
+        else:
+            quantize_all()
+        loss = cnn_hf.forward_and_backward(quantizedModel, data, idx_minibatch, epoch,
+                                           use_distillation_loss=use_distillation_loss, teacher_model=modelToQuantize,
+                                           return_tensor=True)
+        if graphs:
+            graphs[1].replay()
+            grads = graphs[2]
+        else:
+            grads = point_gradients()
+        for pts, gp in zip(pointsPerTensor, grads):
+            pts.grad = gp
+        optimizer.step()
+        for pts in pointsPerTensor:                                       # :550-551, in place: graphs hold pts' address
+            pts.data.copy_(torch.sort(pts.data)[0])
+        return loss, 0, 0
+
+    # whole-step capture (opt-in), same mechanism as train_model(cuda_graph_step=True)
+    whole_ok = bool(cuda_graph_step and device.type == "cuda")
+    side_stream = torch.cuda.Stream(device) if whole_ok else None
+    graphed = None
 
     total_steps, epoch, stop = 0, 0, False
     for epoch in range(epochs_to_train):
         quantizedModel.train()
         running = torch.zeros((), device=device)
         for idx_minibatch, data in enumerate(train_loader, start=1):
-            quantizedModel.zero_grad(set_to_none=False)
-            optimizer.zero_grad(set_to_none=False)
-            if graphs is None and graph_after is not None and total_steps >= graph_after:
-                graphs = _capture_point_graphs(quantize_all, point_gradients, device)
-                if graphs is False:
-                    graph_after = None                                        # capture unavailable: stay eager
-                    graphs = None
-            if graphs:
-                graphs[0].replay()
+            if whole_ok and graphed is None and total_steps >= 3:
+                graphed = _GraphedStep(one_step, data, device, side_stream, optimizer)
+                if not graphed.ok:
+                    whole_ok, graphed = False, None
+            if graphed is not None and graphed.matches(data):
+                loss = graphed.run(data)[0]
+            elif whole_ok:
+                with torch.cuda.stream(side_stream):
+                    loss = one_step(data, idx_minibatch, epoch)[0]
+                torch.cuda.current_stream(device).wait_stream(side_stream)
             else:
-                quantize_all()
-            loss = cnn_hf.forward_and_backward(quantizedModel, data, idx_minibatch, epoch,
-                                               use_distillation_loss=use_distillation_loss,
-                                               teacher_model=modelToQuantize, return_tensor=True)
-            if graphs:
-                graphs[1].replay()
-                grads = graphs[2]
-            else:
-                grads = point_gradients()
-            for pts, gp in zip(pointsPerTensor, grads):
-                pts.grad.data = gp
-            optimizer.step()
-            for pts in pointsPerTensor:                                       # :550-551, in place: the graphs hold pts' address
-                pts.data.copy_(torch.sort(pts.data)[0])
+                loss = one_step(data, idx_minibatch, epoch)[0]
             running += loss
             total_steps += 1
             if step_hook is not None:
@@ -537,6 +558,8 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
         if stop_training is True:
             break
         for group in optimizer.param_groups:
+            if group["lr"] != new_learning_rate:
+                graphed = None                                             # the captured update holds the old rate
             group["lr"] = new_learning_rate
     informationDict = {"predictionAccuracy": pred_accuracy_epochs, "numEpochsTrained": epoch + 1,
                        "lossSaved": losses_epochs, "numStepsTrained": total_steps}

@@ -172,19 +172,20 @@ def test_diffquant_cuda_graph_path_matches_eager(env):
     Q, cfm, hf = env
     torch.backends.cudnn.deterministic = True
     results = []
-    for use_graphs in (False, True):
+    for use_graphs, whole in ((False, False), (True, False), (False, True)):
         torch.manual_seed(11)
         model = make_student(cfm)
-        data = hf.synthetic_cifar_loader(6, 25, seed=9)
+        data = hf.synthetic_cifar_loader(8, 25, seed=9)
         state, points, info = cfm.optimize_quantization_points(
-            model, data, data, initial_learning_rate=1e-3, epochs_to_train=1, print_every=3, numPointsPerTensor=4,
+            model, data, data, initial_learning_rate=1e-3, epochs_to_train=1, print_every=4, numPointsPerTensor=4,
             bucket_size=256, use_distillation_loss=True, initialize_method="quantiles", verbose=False, evaluate=False,
-            use_cuda_graphs=use_graphs)
-        assert info["numStepsTrained"] == 6
+            use_cuda_graphs=use_graphs, cuda_graph_step=whole)
+        assert info["numStepsTrained"] == 8
         results.append([p.detach().clone() for p in points])
     torch.backends.cudnn.deterministic = False
-    for a, b in zip(*results):
+    for a, b, c in zip(*results):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (a, b)
+        assert torch.allclose(a, c, rtol=1e-4, atol=1e-6), (a, c)
     assert any(not torch.equal(a, b0) for a, b0 in zip(results[0], [torch.zeros_like(x) for x in results[0]]))
 
 
