@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -144,21 +145,38 @@ static int launch_warp(const Params& P, bool vec, cudaStream_t s) {
     return vec ? launch_warp_inst<OP, BWD, 8, true>(P, s) : launch_warp_inst<OP, BWD, 8, false>(P, s);
 }
 
-template <int OP, int BWD>
-static int launch_block(const Params& P, cudaStream_t s) {
+template <int OP, int BWD, bool STAGED, int GROUP>
+static int launch_block_inst(const Params& P, cudaStream_t s) {
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    auto kern = block_rows_kernel<OP, BWD>;
-    const size_t smem = (size_t)P.geo.row_len * sizeof(float);
+    auto kern = block_rows_kernel<OP, BWD, STAGED, GROUP>;
+    const size_t smem = STAGED ? (size_t)P.geo.row_len * sizeof(float) : 0;
     if (smem + 8192 > di->smem_optin) return fail(QD_ERR_UNSUPPORTED, "row of %lld floats does not fit in shared memory", (long long)P.geo.row_len);
-    QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (STAGED) QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int occ = resident_ctas(kern, kBlockCtaThreads, smem);
+    constexpr int64_t rows_per_cta = kBlockCtaThreads / GROUP;
+    int64_t need = (P.geo.rows + rows_per_cta - 1) / rows_per_cta;
     int64_t cap = (int64_t)di->sms * occ;
-    int grid = (int)(P.geo.rows < cap ? P.geo.rows : cap);
+    int grid = (int)(need < cap ? need : cap);
     kern<<<grid, kBlockCtaThreads, smem, s>>>(P);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
+}
+
+// thresholds between the three variants (floats per row); QD_WARP2_MAX / QD_STAGED_MAX override them for tuning
+static int64_t env_threshold(const char* name, int64_t dflt) {
+    const char* v = getenv(name);
+    return v ? atoll(v) : dflt;
+}
+
+template <int OP, int BWD>
+static int launch_block(const Params& P, cudaStream_t s) {
+    static const int64_t warp2_max = env_threshold("QD_WARP2_MAX", kWarpTwoPassMaxRow);
+    static const int64_t staged_max = env_threshold("QD_STAGED_MAX", kStagedMaxRow);
+    if (P.geo.row_len <= warp2_max) return launch_block_inst<OP, BWD, false, 32>(P, s);               // warp per row, two passes
+    if (P.geo.row_len <= staged_max) return launch_block_inst<OP, BWD, true, kBlockCtaThreads>(P, s);  // CTA per row, TMA-staged
+    return launch_block_inst<OP, BWD, false, kBlockCtaThreads>(P, s);                                  // CTA per row, L2 re-read
 }
 
 template <int OP, int BWD>

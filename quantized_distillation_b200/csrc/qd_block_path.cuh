@@ -1,14 +1,25 @@
 // qd_block_path.cuh -- rows of 1025 .. QD_MAX_STAGED_BUCKET elements: ONE CTA
-// PER ROW, the row is staged in shared memory so that it still crosses HBM once.
+// (or one warp) PER ROW, still one pass over HBM.  Three variants of the same kernel:
 //
-// Staging uses the TMA bulk-copy engine (cp.async.bulk.shared::cluster.global
-// with mbarrier complete_tx; SASS UBLKCP): one elected thread enqueues the row
-// in 32 KB chunks, each chunk signalling its own mbarrier, and the 512 threads
-// start the min/max reduction of chunk c while chunks c+1.. are still in
-// flight.  Rows whose global address is not 16-byte aligned fall back to a
-// cooperative ld.global -> st.shared copy.  Shared memory is sized to the row
-// (dynamic), so short rows give several resident CTAs per SM and the store
-// phase of one row overlaps the load phase of another.
+// WARP TWO-PASS (rows up to kWarpTwoPassMaxRow floats): a warp streams its row once for
+// min/max and again (L1/L2 hit) for the element-wise pass; no block barrier anywhere, sixteen
+// rows in flight per CTA.
+//
+// STAGED (longer rows): the row is staged in shared memory by
+// the TMA bulk-copy engine (cp.async.bulk.shared::cluster.global with mbarrier
+// complete_tx; SASS UBLKCP): one elected thread enqueues the row in 32 KB
+// chunks, each chunk signalling its own mbarrier, and the 512 threads reduce
+// chunk c while chunks c+1.. are still in flight.  Rows whose global address is
+// not 16-byte aligned fall back to a cooperative ld.global -> st.shared copy.
+// Shared memory is sized to the row (dynamic), so several CTAs are resident per
+// SM and the store phase of one row overlaps the load phase of another.
+//
+// CTA L2 re-read (fallback, selectable with QD_STAGED_MAX): the CTA streams the row
+// once for min/max and again for the element-wise pass; the second read of a
+// <= 192 KB row is an L2 hit, so HBM still sees one read and one write, and no
+// shared memory is needed, so four CTAs per SM overlap each other's phases.
+//
+// All element loops are 128-bit (LDS.128 / LDG.128 / STG.128) with a scalar tail.
 #pragma once
 #include "qd_rowops.cuh"
 
@@ -74,8 +85,56 @@ __device__ __forceinline__ double cta_sum(double v, double* scratch) {
     return warp_sum(r);  // fixed tree: deterministic
 }
 
-template <int OP, int BWD>
+// Measured on B200 (tools/block_bench.py, 64 Mi floats): warp-per-row two-pass wins up to 4096
+// floats per row, the TMA-staged CTA from 8192 up to the 49152-float shared-memory limit; the
+// CTA-wide L2 re-read variant is kept for completeness (QD_STAGED_MAX can select it).
+constexpr int kStagedMaxRow = QD_MAX_STAGED_BUCKET;  // floats; longer rows would use the L2 re-read variant
+constexpr int kWarpTwoPassMaxRow = 4096;  // floats; rows up to here: one WARP per row, two passes (second from L1/L2)
+
+// GROUP = 32: a warp owns the row (no block barriers at all, dozens of rows in flight per SM);
+// GROUP = kBlockCtaThreads: the whole CTA owns the row.
+template <int GROUP, bool IS_MIN>
+__device__ __forceinline__ float grp_minmax(float v, float* scratch) {
+    if constexpr (GROUP == 32) return IS_MIN ? warp_min(v) : warp_max(v);
+    else return cta_minmax<IS_MIN>(v, scratch);
+}
+template <int GROUP>
+__device__ __forceinline__ int grp_min_int(int v, int* scratch) {
+    if constexpr (GROUP == 32) return warp_min_int(v);
+    else return cta_min_int(v, scratch);
+}
+template <int GROUP>
+__device__ __forceinline__ double grp_sum(double v, double* scratch) {
+    if constexpr (GROUP == 32) return warp_sum(v);
+    else return cta_sum(v, scratch);
+}
+
+// Calls f4(e, float4) on aligned groups of four elements and f1(e, float) on the tail (or on
+// every element when the global row is not 16-byte aligned and not staged).
+template <bool STAGED, int GROUP, class F4, class F1>
+__device__ __forceinline__ void for_each_in_row(const float* s_row, const float* src, int len, bool gvec, bool pre,
+                                                float mean, float max_el, F4 f4, F1 f1) {
+    const int gtid = (GROUP == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    const int len4 = (STAGED || gvec) ? (len & ~3) : 0;
+#pragma unroll 2
+    for (int e = gtid * 4; e < len4; e += GROUP * 4) {
+        float4 t = STAGED ? *reinterpret_cast<const float4*>(s_row + e) : *reinterpret_cast<const float4*>(src + e);
+        if (!STAGED && pre) {
+            t.x = pre_op(t.x, mean, max_el); t.y = pre_op(t.y, mean, max_el);
+            t.z = pre_op(t.z, mean, max_el); t.w = pre_op(t.w, mean, max_el);
+        }
+        f4(e, t);
+    }
+    for (int e = len4 + gtid; e < len; e += GROUP) {
+        float t = STAGED ? s_row[e] : src[e];
+        if (!STAGED && pre) t = pre_op(t, mean, max_el);
+        f1(e, t);
+    }
+}
+
+template <int OP, int BWD, bool STAGED, int GROUP>
 __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __grid_constant__ Params P) {
+    static_assert(!(STAGED && GROUP == 32), "staging is a CTA-wide operation");
     extern __shared__ __align__(128) float s_row[];
     __shared__ __align__(8) uint64_t s_bar[kMaxStageChunks];
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
@@ -84,66 +143,92 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
 
     Centroids cen{s_k, s_m, P.num_points};
     if constexpr (OP == OP_NONUNIFORM) centroid_setup(s_k, s_m, P.points, P.num_points);
-    if (threadIdx.x == 0) {
+    if (STAGED && threadIdx.x == 0) {
         for (int c = 0; c < kMaxStageChunks; ++c) mbar_init(&s_bar[c], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const int tid = threadIdx.x;
+    const int tid = (GROUP == 32) ? (threadIdx.x & 31) : threadIdx.x;
     const bool pre = (P.mean != nullptr) || (P.max_element > 0.f);
     const float mean = P.mean ? *P.mean : 0.f;
+    const float max_el = P.max_element;
     uint32_t phase_bits = 0;  // bit c = parity the next wait on s_bar[c] must see
+    constexpr int kGroups = kBlockCtaThreads / GROUP;  // rows in flight per CTA
 
-    for (int64_t row = blockIdx.x; row < P.geo.rows; row += gridDim.x) {
+    for (int64_t row = (int64_t)blockIdx.x * kGroups + (GROUP == 32 ? (threadIdx.x >> 5) : 0); row < P.geo.rows;
+         row += (int64_t)gridDim.x * kGroups) {
         const int64_t base = row * P.geo.row_len;
         const int len = (int)min(P.geo.row_len, P.geo.n - base);
         const float* src = P.x + base;
-        const bool tma_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-        const int bulk_len = tma_ok ? (len & ~3) : 0;  // multiple of 16 bytes
-        const int nchunks = (bulk_len + kStageChunk - 1) / kStageChunk;
+        const bool gvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        // 128-bit stores need every output row to be 16-byte aligned too
+        const bool ovec = (((reinterpret_cast<uintptr_t>(P.q + base) | reinterpret_cast<uintptr_t>(P.gout + base) |
+                             reinterpret_cast<uintptr_t>(P.g + base) | reinterpret_cast<uintptr_t>(P.xhat + base)) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(P.idx8 + base) & 3) == 0);
 
-        // ---- stage the row -------------------------------------------------
-        if (tid == 0 && nchunks > 0) {
-            // generic-proxy reads of the previous row are complete (barrier at loop end);
-            // order them before the async-proxy writes that follow
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int c = 0; c < nchunks; ++c) {
-                const int off = c * kStageChunk;
-                const uint32_t bytes = (uint32_t)min(kStageChunk, bulk_len - off) * 4u;
-                mbar_expect_tx(&s_bar[c], bytes);
-                tma_bulk_g2s(s_row + off, src + off, bytes, &s_bar[c]);
-            }
-        }
-        for (int e = bulk_len + tid; e < len; e += kBlockCtaThreads) s_row[e] = ld_stream1(src + e);
-
-        // ---- min / max, chunk by chunk as the copies land ---------------------
         float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-        for (int c = 0; c < nchunks; ++c) {
-            mbar_wait(&s_bar[c], (phase_bits >> c) & 1u);
-            phase_bits ^= (1u << c);
-            const int off = c * kStageChunk;
-            const int cl = min(kStageChunk, bulk_len - off);
-            for (int e = tid * 4; e < cl; e += kBlockCtaThreads * 4) {
-                float4 t = *reinterpret_cast<const float4*>(s_row + off + e);
+        if constexpr (STAGED) {
+            const int bulk_len = gvec ? (len & ~3) : 0;  // multiple of 16 bytes
+            const int nchunks = (bulk_len + kStageChunk - 1) / kStageChunk;
+            if (tid == 0 && nchunks > 0) {
+                // generic-proxy reads of the previous row are complete (barrier at loop end);
+                // order them before the async-proxy writes that follow
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                for (int c = 0; c < nchunks; ++c) {
+                    const int off = c * kStageChunk;
+                    const uint32_t bytes = (uint32_t)min(kStageChunk, bulk_len - off) * 4u;
+                    mbar_expect_tx(&s_bar[c], bytes);
+                    tma_bulk_g2s(s_row + off, src + off, bytes, &s_bar[c]);
+                }
+            }
+            for (int e = bulk_len + tid; e < len; e += kBlockCtaThreads) s_row[e] = ld_stream1(src + e);
+            // min / max, chunk by chunk as the copies land
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(&s_bar[c], (phase_bits >> c) & 1u);
+                phase_bits ^= (1u << c);
+                const int off = c * kStageChunk;
+                const int cl = min(kStageChunk, bulk_len - off);
+                for (int e = tid * 4; e < cl; e += kBlockCtaThreads * 4) {
+                    float4 t = *reinterpret_cast<const float4*>(s_row + off + e);
+                    if (pre) {
+                        t.x = pre_op(t.x, mean, max_el); t.y = pre_op(t.y, mean, max_el);
+                        t.z = pre_op(t.z, mean, max_el); t.w = pre_op(t.w, mean, max_el);
+                        *reinterpret_cast<float4*>(s_row + off + e) = t;
+                    }
+                    mn = min_nan(min_nan(mn, t.x), min_nan(t.y, min_nan(t.z, t.w)));
+                    mx = max_nan(max_nan(mx, t.x), max_nan(t.y, max_nan(t.z, t.w)));
+                }
+            }
+            __syncthreads();  // scalar-staged tail visible
+            for (int e = bulk_len + tid; e < len; e += kBlockCtaThreads) {
+                float t = s_row[e];
+                if (pre) { t = pre_op(t, mean, max_el); s_row[e] = t; }
+                mn = min_nan(mn, t);
+                mx = max_nan(mx, t);
+            }
+        } else {
+            // first pass over the row from HBM (it stays in L2 for the passes below)
+            const int len4 = gvec ? (len & ~3) : 0;
+#pragma unroll 4
+            for (int e = tid * 4; e < len4; e += GROUP * 4) {
+                float4 t = ld_stream4(src + e);
                 if (pre) {
-                    t.x = pre_op(t.x, mean, P.max_element); t.y = pre_op(t.y, mean, P.max_element);
-                    t.z = pre_op(t.z, mean, P.max_element); t.w = pre_op(t.w, mean, P.max_element);
-                    *reinterpret_cast<float4*>(s_row + off + e) = t;
+                    t.x = pre_op(t.x, mean, max_el); t.y = pre_op(t.y, mean, max_el);
+                    t.z = pre_op(t.z, mean, max_el); t.w = pre_op(t.w, mean, max_el);
                 }
                 mn = min_nan(min_nan(mn, t.x), min_nan(t.y, min_nan(t.z, t.w)));
                 mx = max_nan(max_nan(mx, t.x), max_nan(t.y, max_nan(t.z, t.w)));
             }
+            for (int e = len4 + tid; e < len; e += GROUP) {
+                float t = ld_stream1(src + e);
+                if (pre) t = pre_op(t, mean, max_el);
+                mn = min_nan(mn, t);
+                mx = max_nan(mx, t);
+            }
         }
-        __syncthreads();  // scalar-staged tail visible
-        for (int e = bulk_len + tid; e < len; e += kBlockCtaThreads) {
-            float t = s_row[e];
-            if (pre) { t = pre_op(t, mean, P.max_element); s_row[e] = t; }
-            mn = min_nan(mn, t);
-            mx = max_nan(mx, t);
-        }
-        mn = cta_minmax<true>(mn, reinterpret_cast<float*>(s_scratch));
-        mx = cta_minmax<false>(mx, reinterpret_cast<float*>(s_scratch));
+        mn = grp_minmax<GROUP, true>(mn, reinterpret_cast<float*>(s_scratch));
+        mx = grp_minmax<GROUP, false>(mx, reinterpret_cast<float*>(s_scratch));
         RowState rs;
         rs.mean = mean;
         rs.beta = mn;
@@ -151,91 +236,155 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
         if (P.alpha != nullptr && tid == 0) { P.alpha[row] = rs.alpha; P.beta[row] = rs.beta; }
         if (P.argmin != nullptr) {
             int imin = 0x7fffffff, imax = 0x7fffffff;
-            for (int e = tid; e < len; e += kBlockCtaThreads) {
-                float t = s_row[e];
+            auto scan1 = [&](int e, float t) {
                 if (t == mn) imin = min(imin, e);
                 if (t == mx) imax = min(imax, e);
-            }
-            imin = cta_min_int(imin, reinterpret_cast<int*>(s_scratch));
-            imax = cta_min_int(imax, reinterpret_cast<int*>(s_scratch));
+            };
+            for_each_in_row<STAGED, GROUP>(s_row, src, len, gvec, pre, mean, max_el,
+                                    [&](int e, float4 t) { scan1(e, t.x); scan1(e + 1, t.y); scan1(e + 2, t.z); scan1(e + 3, t.w); },
+                                    scan1);
+            imin = grp_min_int<GROUP>(imin, reinterpret_cast<int*>(s_scratch));
+            imax = grp_min_int<GROUP>(imax, reinterpret_cast<int*>(s_scratch));
             if (tid == 0) {
                 P.argmin[row] = (imin == 0x7fffffff) ? 0 : imin;
                 P.argmax[row] = (imax == 0x7fffffff) ? 0 : imax;
             }
         }
 
-        // ---- element-wise pass from shared memory ----------------------------
+        // ---- element-wise pass ---------------------------------------------------
         if constexpr (OP == OP_SCALE) {
-            const int plen = (int)P.geo.row_len;
-            const float last = to_unit(s_row[len - 1], rs.beta, rs.alpha);
+            const int plen = (int)P.geo.row_len;  // padded layout: the tail repeats x_hat of the last element
+            float lastv = STAGED ? s_row[len - 1] : src[len - 1];
+            if (!STAGED && pre) lastv = pre_op(lastv, mean, max_el);
+            const float last = to_unit(lastv, rs.beta, rs.alpha);
             float* dst = P.xhat + base;
-            for (int e = tid; e < plen; e += kBlockCtaThreads)
-                st_stream1(dst + e, e < len ? to_unit(s_row[e], rs.beta, rs.alpha) : last);
+            for_each_in_row<STAGED, GROUP>(s_row, src, len, gvec, pre, mean, max_el,
+                                    [&](int e, float4 t) {
+                                        float4 o = make_float4(to_unit(t.x, rs.beta, rs.alpha), to_unit(t.y, rs.beta, rs.alpha),
+                                                               to_unit(t.z, rs.beta, rs.alpha), to_unit(t.w, rs.beta, rs.alpha));
+                                        if (ovec) st_stream4(dst + e, o);
+                                        else { dst[e] = o.x; dst[e + 1] = o.y; dst[e + 2] = o.z; dst[e + 3] = o.w; }
+                                    },
+                                    [&](int e, float t) { dst[e] = to_unit(t, rs.beta, rs.alpha); });
+            for (int e = len + tid; e < plen; e += GROUP) dst[e] = last;
         } else if constexpr (OP == OP_UNIFORM) {
             float rb = 0.f;
             int imin2 = 0, imax2 = 0;
             const UniformFast uf = make_uniform_fast(rs.alpha, P.S);
-            if constexpr (BWD == BWD_MINMAX) {
-                float qmn = __int_as_float(0x7f800000), qmx = __int_as_float(0xff800000);
-                for (int e = tid; e < len; e += kBlockCtaThreads) {
-                    float lvl;
-                    float qv = uniform_quantize(s_row[e], rs, P.S, lvl);
-                    qmn = min_nan(qmn, qv);
-                    qmx = max_nan(qmx, qv);
-                }
-                qmn = cta_minmax<true>(qmn, reinterpret_cast<float*>(s_scratch));
-                qmx = cta_minmax<false>(qmx, reinterpret_cast<float*>(s_scratch));
-                rs.beta2 = qmn;
-                rs.alpha2 = make_alpha(qmn, qmx);
-                double acc = 0.0;
-                imin2 = 0x7fffffff; imax2 = 0x7fffffff;
-                for (int e = tid; e < len; e += kBlockCtaThreads) {
-                    float lvl;
-                    float xv = s_row[e];
-                    float qv = uniform_quantize(xv, rs, P.S, lvl);
-                    if (qv == qmn) imin2 = min(imin2, e);
-                    if (qv == qmx) imax2 = min(imax2, e);
-                    acc += (double)minmax_term(xv, qv, P.g[base + e], rs);
-                }
-                imin2 = cta_min_int(imin2, reinterpret_cast<int*>(s_scratch));
-                imax2 = cta_min_int(imax2, reinterpret_cast<int*>(s_scratch));
-                rb = (float)cta_sum(acc, s_scratch);
-            }
-            for (int e = tid; e < len; e += kBlockCtaThreads) {
-                float lvl, qv;
-                const float xv = s_row[e];
+            auto quant = [&](float xv, int64_t ge, float& lvl) -> float {
                 if (P.stochastic) {
                     Philox rng(P.seed);
-                    const int64_t ge = base + e;
                     uint4 rnd = rng(P.offset + (uint64_t)(ge >> 2));
                     uint32_t w = (ge & 3) == 0 ? rnd.x : (ge & 3) == 1 ? rnd.y : (ge & 3) == 2 ? rnd.z : rnd.w;
-                    qv = uniform_quantize_stochastic(xv, rs, P.S, u01(w), lvl);
-                } else {
-                    qv = uniform_quantize_auto(xv, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+                    return uniform_quantize_stochastic(xv, rs, P.S, u01(w), lvl);
                 }
-                if constexpr (BWD != BWD_OFF) {
-                    float gv = P.g[base + e];
-                    if constexpr (BWD == BWD_TRUNC) gv = (fabsf(xv) > 1.0f) ? 0.f : gv;
-                    if (BWD == BWD_MINMAX && imin2 != imax2) {
-                        if (e == imax2) gv = __fadd_rn(gv, rb);
-                        if (e == imin2) gv = __fadd_rn(gv, -rb);
+                return uniform_quantize_auto(xv, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+            };
+            if constexpr (BWD == BWD_MINMAX) {
+                // second scaling of the quantized row (quant_functions.py:350-363), see the warp path
+                float qmn = __int_as_float(0x7f800000), qmx = __int_as_float(0xff800000);
+                auto q1 = [&](int e, float t) {
+                    float lvl;
+                    const float qv = quant(t, base + e, lvl);
+                    qmn = min_nan(qmn, qv);
+                    qmx = max_nan(qmx, qv);
+                };
+                for_each_in_row<STAGED, GROUP>(s_row, src, len, gvec, pre, mean, max_el,
+                                        [&](int e, float4 t) { q1(e, t.x); q1(e + 1, t.y); q1(e + 2, t.z); q1(e + 3, t.w); }, q1);
+                qmn = grp_minmax<GROUP, true>(qmn, reinterpret_cast<float*>(s_scratch));
+                qmx = grp_minmax<GROUP, false>(qmx, reinterpret_cast<float*>(s_scratch));
+                rs.beta2 = qmn;
+                rs.alpha2 = make_alpha(qmn, qmx);
+                const RowDivider div2(rs.alpha2);
+                double acc = 0.0;
+                imin2 = 0x7fffffff; imax2 = 0x7fffffff;
+                auto q2 = [&](int e, float t) {
+                    float lvl;
+                    const float qv = quant(t, base + e, lvl);
+                    if (qv == qmn) imin2 = min(imin2, e);
+                    if (qv == qmx) imax2 = min(imax2, e);
+                    acc += (double)minmax_term(t, qv, P.g[base + e], rs.beta2, div2);
+                };
+                for_each_in_row<STAGED, GROUP>(s_row, src, len, gvec, pre, mean, max_el,
+                                        [&](int e, float4 t) { q2(e, t.x); q2(e + 1, t.y); q2(e + 2, t.z); q2(e + 3, t.w); }, q2);
+                imin2 = grp_min_int<GROUP>(imin2, reinterpret_cast<int*>(s_scratch));
+                imax2 = grp_min_int<GROUP>(imax2, reinterpret_cast<int*>(s_scratch));
+                rb = (float)grp_sum<GROUP>(acc, s_scratch);
+            }
+            auto fix = [&](int e, float xv, float gv) -> float {
+                if constexpr (BWD == BWD_TRUNC) gv = (fabsf(xv) > 1.0f) ? 0.f : gv;
+                if (BWD == BWD_MINMAX && imin2 != imax2) {
+                    if (e == imax2) gv = __fadd_rn(gv, rb);
+                    if (e == imin2) gv = __fadd_rn(gv, -rb);
+                }
+                return gv;
+            };
+            for_each_in_row<STAGED, GROUP>(
+                s_row, src, len, gvec, pre, mean, max_el,
+                [&](int e, float4 t) {
+                    float lv[4];
+                    float4 qo = make_float4(quant(t.x, base + e, lv[0]), quant(t.y, base + e + 1, lv[1]),
+                                            quant(t.z, base + e + 2, lv[2]), quant(t.w, base + e + 3, lv[3]));
+                    if (pre) { qo.x = __fadd_rn(qo.x, mean); qo.y = __fadd_rn(qo.y, mean); qo.z = __fadd_rn(qo.z, mean); qo.w = __fadd_rn(qo.w, mean); }
+                    if constexpr (BWD != BWD_OFF) {
+                        float4 gv = ovec ? *reinterpret_cast<const float4*>(P.g + base + e)
+                                         : make_float4(P.g[base + e], P.g[base + e + 1], P.g[base + e + 2], P.g[base + e + 3]);
+                        gv.x = fix(e, t.x, gv.x); gv.y = fix(e + 1, t.y, gv.y); gv.z = fix(e + 2, t.z, gv.z); gv.w = fix(e + 3, t.w, gv.w);
+                        if (ovec) st_stream4(P.gout + base + e, gv);
+                        else { P.gout[base + e] = gv.x; P.gout[base + e + 1] = gv.y; P.gout[base + e + 2] = gv.z; P.gout[base + e + 3] = gv.w; }
                     }
-                    st_stream1(P.gout + base + e, gv);
-                }
-                if (P.q != nullptr) st_stream1(P.q + base + e, pre ? __fadd_rn(qv, mean) : qv);
-                if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)(int)lvl;
-            }
+                    if (P.q != nullptr) {
+                        if (ovec) st_stream4(P.q + base + e, qo);
+                        else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
+                    }
+                    if (P.idx8 != nullptr) {
+                        if (ovec) *reinterpret_cast<uint32_t*>(P.idx8 + base + e) =
+                                (uint32_t)(int)lv[0] | ((uint32_t)(int)lv[1] << 8) | ((uint32_t)(int)lv[2] << 16) | ((uint32_t)(int)lv[3] << 24);
+                        else for (int j = 0; j < 4; ++j) P.idx8[base + e + j] = (uint8_t)(int)lv[j];
+                    }
+                },
+                [&](int e, float t) {
+                    float lvl;
+                    float qv = quant(t, base + e, lvl);
+                    if (pre) qv = __fadd_rn(qv, mean);
+                    if constexpr (BWD != BWD_OFF) P.gout[base + e] = fix(e, t, P.g[base + e]);
+                    if (P.q != nullptr) P.q[base + e] = qv;
+                    if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)(int)lvl;
+                });
         } else if constexpr (OP == OP_NONUNIFORM) {
-            for (int e = tid; e < len; e += kBlockCtaThreads) {
-                float xh = to_unit(s_row[e], rs.beta, rs.alpha);
-                int id = centroid_index(cen, xh, P.rule);
-                float qv = from_unit(cen.k[id], rs.alpha, rs.beta);
-                if (P.q != nullptr) st_stream1(P.q + base + e, pre ? __fadd_rn(qv, mean) : qv);
-                if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)id;
-                if (P.idx64 != nullptr) P.idx64[base + e] = id;
-            }
+            const RowDivider div(rs.alpha);
+            auto one = [&](int e, float t, float& qv) -> int {
+                const float xh = div.exact(__fsub_rn(t, rs.beta));
+                float kval;
+                const int id = smem_index<256>(cen.k, cen.m, cen.K, xh, P.rule, kval);
+                qv = from_unit(kval, rs.alpha, rs.beta);
+                if (pre) qv = __fadd_rn(qv, mean);
+                return id;
+            };
+            for_each_in_row<STAGED, GROUP>(
+                s_row, src, len, gvec, pre, mean, max_el,
+                [&](int e, float4 t) {
+                    float4 qo;
+                    const int i0 = one(e, t.x, qo.x), i1 = one(e + 1, t.y, qo.y), i2 = one(e + 2, t.z, qo.z), i3 = one(e + 3, t.w, qo.w);
+                    if (P.q != nullptr) {
+                        if (ovec) st_stream4(P.q + base + e, qo);
+                        else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
+                    }
+                    if (P.idx8 != nullptr) {
+                        if (ovec) *reinterpret_cast<uint32_t*>(P.idx8 + base + e) = (uint32_t)i0 | ((uint32_t)i1 << 8) | ((uint32_t)i2 << 16) | ((uint32_t)i3 << 24);
+                        else { P.idx8[base + e] = (uint8_t)i0; P.idx8[base + e + 1] = (uint8_t)i1; P.idx8[base + e + 2] = (uint8_t)i2; P.idx8[base + e + 3] = (uint8_t)i3; }
+                    }
+                    if (P.idx64 != nullptr) { P.idx64[base + e] = i0; P.idx64[base + e + 1] = i1; P.idx64[base + e + 2] = i2; P.idx64[base + e + 3] = i3; }
+                },
+                [&](int e, float t) {
+                    float qv;
+                    const int id = one(e, t, qv);
+                    if (P.q != nullptr) P.q[base + e] = qv;
+                    if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)id;
+                    if (P.idx64 != nullptr) P.idx64[base + e] = id;
+                });
         }
-        __syncthreads();  // everyone is done with s_row before the next row is staged
+        if constexpr (GROUP != 32) __syncthreads();  // everyone is done with the row (and s_row) before the next one
     }
 }
 
