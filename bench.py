@@ -70,6 +70,33 @@ class ClockSampler(threading.Thread):
         except Exception as e:                      # pragma: no cover - NVML missing
             self.err = str(e)
 
+    def sample_once(self):
+        """One synchronous sample (called while the timed region's work is queued on the GPU)."""
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self._names().items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _names(self):
+        nv = self.nv
+        return {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+
     def run(self):
         if not self.ok:
             return
@@ -341,6 +368,9 @@ def main():
     for _ in range(steps):
         step()
     ev1.record(stream)
+    while not ev1.query():              # the K steps are queued: sample the clocks while they execute
+        sampler.sample_once()
+        time.sleep(0.002)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()

@@ -380,7 +380,9 @@ constexpr bool kPrefetchNextRow = (OP != OP_UNIFORM) || (AUX == (int)BWD_OFF);
 // (measured per kernel: the forward-only and min/max kernels gain, STE / truncated / non-uniform
 // are better with ptxas's own choice, 0 = unconstrained)
 template <int OP, int AUX, int R>
-constexpr int kMinCtas = (OP == OP_UNIFORM && R == 2 && (AUX == (int)BWD_OFF || AUX == (int)BWD_MINMAX)) ? 4 : 0;
+constexpr int kMinCtas = (OP == OP_UNIFORM && R == 2 && (AUX == (int)BWD_OFF || AUX == (int)BWD_MINMAX)) ? 4
+                         : (OP == OP_UNIFORM && R == 8 && AUX != (int)BWD_OFF) ? 2   // 1024-element rows with a gradient: cap at 128 regs
+                                                                               : 0;
 
 template <int OP, int AUX, int R, bool VEC>
 __global__ void __launch_bounds__(kWarpCtaThreads, kMinCtas<OP, AUX, R>) warp_rows_kernel(const __grid_constant__ Params P) {
