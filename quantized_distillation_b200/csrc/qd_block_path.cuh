@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
             auto one = [&](int e, float t, float& qv) -> int {
                 const float xh = div.exact(__fsub_rn(t, rs.beta));
                 float kval;
-                const int id = smem_index<256>(cen.k, cen.m, cen.K, xh, P.rule, kval);
+                const int id = (P.rule == QD_RULE_MIDPOINT) ? smem_index<256, true>(cen.k, cen.m, cen.K, xh, kval)
+                                                            : smem_index<256, false>(cen.k, cen.m, cen.K, xh, kval);
                 qv = from_unit(kval, rs.alpha, rs.beta);
                 if (pre) qv = __fadd_rn(qv, mean);
                 return id;

@@ -330,19 +330,27 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
 #pragma unroll
             for (int i = 0; i < E; ++i) xh[i] = RowDivider::slow_div(__fsub_rn(v[i], rs.beta), rs.alpha);
         }
+        // the rule is uniform for the launch: branch once per row, not once per element
+        if (P.rule == QD_RULE_MIDPOINT) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) {
-            float kval;
-            if constexpr (KR > 8) {
-                li[i] = smem_index<KR>(cen.k, cen.m, cen.K, xh[i], P.rule, kval);
-            } else if constexpr (KR > 0) {
-                li[i] = rt.index(xh[i], P.rule, cen.K, kval);
-            } else {
-                li[i] = centroid_index(cen, xh[i], P.rule);
-                kval = cen.k[li[i]];
+            for (int i = 0; i < E; ++i) {
+                float kval;
+                if constexpr (KR > 8) li[i] = smem_index<KR, true>(cen.k, cen.m, cen.K, xh[i], kval);
+                else li[i] = rt.template index<true>(xh[i], cen.K, kval);
+                qv[i] = from_unit(kval, rs.alpha, rs.beta);
             }
-            qv[i] = from_unit(kval, rs.alpha, rs.beta);
-            if (pre) qv[i] = __fadd_rn(qv[i], rs.mean);
+        } else {
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                float kval;
+                if constexpr (KR > 8) li[i] = smem_index<KR, false>(cen.k, cen.m, cen.K, xh[i], kval);
+                else li[i] = rt.template index<false>(xh[i], cen.K, kval);
+                qv[i] = from_unit(kval, rs.alpha, rs.beta);
+            }
+        }
+        if (pre) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) qv[i] = __fadd_rn(qv[i], rs.mean);
         }
         if (P.q != nullptr) store_row<R, VEC, FULL>(P.q + base, len, lane, qv);
         if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, li);
