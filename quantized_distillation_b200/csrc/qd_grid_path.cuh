@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
         rs.alpha = rowstat[row].alpha;
         rs.beta = rowstat[row].beta;
         const UniformFast uf = make_uniform_fast(rs.alpha, P.S);
+        const RowDivider rowdiv(rs.alpha);
+        const bool mid_rule = (P.rule == QD_RULE_MIDPOINT);
         if constexpr (OP == OP_SCALE) {
             // padded layout: positions past the end of the tail row repeat x_hat of the last element
             const int plen = (int)min((int64_t)kGridChunk, P.geo.row_len - off);
@@ -234,11 +236,19 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                         qv[j] = uniform_quantize_auto(t, rs, uf, P.S, P.rS, P.half_minus_band, lv[j]);
                     }
                     if constexpr (BWD == BWD_TRUNC) gv[j] = (fabsf(t) > 1.0f) ? 0.f : gv[j];
-                } else {  // OP_NONUNIFORM
-                    float xh = to_unit(t, rs.beta, rs.alpha);
-                    int id = centroid_index(cen, xh, P.rule);
+                } else {  // OP_NONUNIFORM: exact x_hat through the hoisted reciprocal, unrolled table search
+                    const float xh = rowdiv.exact(__fsub_rn(t, rs.beta));
+                    float kval;
+                    int id;
+                    if (cen.K <= 4) {
+                        id = mid_rule ? smem_index<4, true>(cen.k, cen.m, cen.K, xh, kval) : smem_index<4, false>(cen.k, cen.m, cen.K, xh, kval);
+                    } else if (cen.K <= 16) {
+                        id = mid_rule ? smem_index<16, true>(cen.k, cen.m, cen.K, xh, kval) : smem_index<16, false>(cen.k, cen.m, cen.K, xh, kval);
+                    } else {
+                        id = mid_rule ? smem_index<256, true>(cen.k, cen.m, cen.K, xh, kval) : smem_index<256, false>(cen.k, cen.m, cen.K, xh, kval);
+                    }
                     lv[j] = (float)id;
-                    qv[j] = from_unit(cen.k[id], rs.alpha, rs.beta);
+                    qv[j] = from_unit(kval, rs.alpha, rs.beta);
                 }
                 if (pre) qv[j] = __fadd_rn(qv[j], mean);
             }

@@ -555,3 +555,36 @@ def test_size_accounting_matches_reference_formula(Q):
     count_u = params[0].numel() + params[-1].numel()
     assert abs(mb - (count_u * 4 + mbl * count_q / 8 + count_q / 256 * 8) / 1e6) < 1e-12
     assert codec.get_size_quantized_model(model, None, fun) == sum(p.numel() for p in params) * 4 / 1e6
+
+
+def test_c_abi_is_reentrant_across_threads_and_streams(Q):
+    """Four Python threads, each on its own CUDA stream, hammer the library concurrently;
+    every result must equal the single-threaded one (no shared mutable state in the ABI)."""
+    import threading
+    rng = np.random.default_rng(53)
+    xs = [dev((rng.standard_normal(200_003) * 0.05).astype(np.float32)) for _ in range(4)]
+    expect = [Q.uniformQuantization(x, 16, bucket_size=256)[0].clone() for x in xs]
+    expect_none = [Q.uniformQuantization(x, 16, bucket_size=None)[0].clone() for x in xs]
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    q, _ = Q.uniformQuantization(xs[i], 16, bucket_size=256)
+                    qn, _ = Q.uniformQuantization(xs[i], 16, bucket_size=None)       # grid path: needs its own workspace
+                    f = Q.nonUniformQuantization_variable(bucket_size=256, pre_process_tensors=True, tensor=xs[i])
+                    f.forward(None, torch.linspace(0, 1, 4, device="cuda"))
+                    f.backward(xs[i])
+                s.synchronize()
+                if not (torch.equal(q, expect[i]) and torch.equal(qn, expect_none[i])):
+                    errors.append(i)
+        except Exception as e:  # pragma: no cover
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
