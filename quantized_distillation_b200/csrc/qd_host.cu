@@ -6,15 +6,23 @@
 // PCIe direction, not by their sum.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "qd_b200.h"
 
 namespace {
 
-constexpr int kSlots = 3;
-constexpr int64_t kChunkElems = 4 << 20;  // 16 MiB per buffer
+constexpr int kMaxSlots = 8;
+// chunk size / pipeline depth, overridable for tuning (QD_HOST_CHUNK_ELEMS, QD_HOST_SLOTS)
+static int64_t env_i64(const char* name, int64_t dflt) {
+    const char* v = getenv(name);
+    return v ? atoll(v) : dflt;
+}
+static const int kSlots = (int)std::min<int64_t>(kMaxSlots, std::max<int64_t>(1, env_i64("QD_HOST_SLOTS", 3)));
+static const int64_t kChunkElems = std::max<int64_t>(1 << 16, env_i64("QD_HOST_CHUNK_ELEMS", 4 << 20));  // 16 MiB per buffer
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -25,7 +33,7 @@ struct Slot {
 
 struct HostCtx {
     bool ready = false;
-    Slot slot[kSlots];
+    Slot slot[kMaxSlots];
     float *big_x = nullptr, *big_g = nullptr, *big_q = nullptr, *big_gout = nullptr;  // bucket=None path
     int64_t big_cap = 0;
     void* big_ws = nullptr;
