@@ -318,6 +318,8 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
         // sequence's proven domain (see RowDivider)
         const RowDivider div(rs.alpha);
         const float thr = div.thr();
+        Pivot16 pv16;
+        if constexpr (KR == 16) pv16.load(cen);      // six broadcast loads per row, hoisted out of the element loop
         float xh[E];
         bool unsafe = !div.ok;
 #pragma unroll
@@ -335,7 +337,8 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 float kval;
-                if constexpr (KR > 8) li[i] = smem_index<KR, true>(cen.k, cen.m, cen.K, xh[i], kval);
+                if constexpr (KR == 16) li[i] = pivot_index16<true>(cen.k, cen.m, pv16, cen.K, xh[i], kval);
+                else if constexpr (KR > 8) li[i] = smem_index<KR, true>(cen.k, cen.m, cen.K, xh[i], kval);
                 else li[i] = rt.template index<true>(xh[i], cen.K, kval);
                 qv[i] = from_unit(kval, rs.alpha, rs.beta);
             }
@@ -343,7 +346,8 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 float kval;
-                if constexpr (KR > 8) li[i] = smem_index<KR, false>(cen.k, cen.m, cen.K, xh[i], kval);
+                if constexpr (KR == 16) li[i] = pivot_index16<false>(cen.k, cen.m, pv16, cen.K, xh[i], kval);
+                else if constexpr (KR > 8) li[i] = smem_index<KR, false>(cen.k, cen.m, cen.K, xh[i], kval);
                 else li[i] = rt.template index<false>(xh[i], cen.K, kval);
                 qv[i] = from_unit(kval, rs.alpha, rs.beta);
             }
@@ -394,8 +398,8 @@ constexpr int kMinCtas = (OP == OP_UNIFORM && R == 2 && (AUX == (int)BWD_OFF || 
 
 template <int OP, int AUX, int R, bool VEC>
 __global__ void __launch_bounds__(kWarpCtaThreads, kMinCtas<OP, AUX, R>) warp_rows_kernel(const __grid_constant__ Params P) {
-    __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
-    __shared__ float s_m[OP == OP_NONUNIFORM ? 256 : 1];
+    __shared__ __align__(16) float s_k[OP == OP_NONUNIFORM ? 256 : 1];   // 16-byte aligned: read as float4 groups
+    __shared__ __align__(16) float s_m[OP == OP_NONUNIFORM ? 256 : 1];
     Centroids cen{s_k, s_m, P.num_points};
     RegTable<(OP == OP_NONUNIFORM && AUX <= 8 ? AUX : 0)> rt;
     if constexpr (OP == OP_NONUNIFORM) {
