@@ -102,21 +102,37 @@ def stream_ptr(device=None):
 
 
 _ws = {}
+_WS_FLOOR = 1 << 22          # covers every op whose rows are staged on chip (qd_workspace_bytes <= ~2.5 MB)
 
 
 def workspace(n: int, bucket: int, device) -> torch.Tensor:
     """Per (device, stream) scratch buffer, grown on demand."""
-    need = int(lib().qd_workspace_bytes(n, bucket))
+    # only rows longer than the staging limit (grid path) can need more than the floor
+    need = _WS_FLOOR
+    if (bucket == 0 or bucket > MAX_STAGED_BUCKET) and n > MAX_STAGED_BUCKET:
+        need = max(need, int(lib().qd_workspace_bytes(n, bucket)))
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
     buf = _ws.get(key)
     if buf is None or buf.numel() < need:
-        buf = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=device)
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
 
 
 def geometry(n: int, bucket: int):
+    """(rows, row_len, padded_len) of create_bucket_tensor (help_functions.py:67-94); same
+    arithmetic as qd_bucket_geometry, kept in Python to save an FFI round trip per call
+    (tests/test_cpu_boundary.py checks the two against each other and against the oracle)."""
+    if n <= 0 or bucket < 0:
+        raise ValueError(f"n must be > 0 and bucket >= 0 (n={n} bucket={bucket})")
+    if bucket == 0 or n < bucket:
+        return 1, n, n
+    rows = -(-n // bucket)
+    return rows, bucket, rows * bucket
+
+
+def geometry_native(n: int, bucket: int):
     rows, row_len, padded = _i64(), _i64(), _i64()
     check(lib().qd_bucket_geometry(n, bucket, C.byref(rows), C.byref(row_len), C.byref(padded)))
     return rows.value, row_len.value, padded.value

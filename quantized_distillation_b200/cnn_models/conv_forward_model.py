@@ -436,8 +436,9 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
                                         use_distillation_loss=False, return_tensor=True)
             if idx_minibatch >= num_to_estimate_grad:
                 break
-        norms = [float((p.grad / num_to_estimate_grad).norm())
-                 for p in _selected_parameters(modelToQuantize, quantize_first_and_last_layer)]
+        # ||grad / num||_2 of every selected tensor: one multi-tensor launch, one device->host copy
+        sel_grads = [p.grad for p in _selected_parameters(modelToQuantize, quantize_first_and_last_layer)]
+        norms = (torch.stack(torch._foreach_norm(sel_grads)) / num_to_estimate_grad).tolist()
         modelToQuantize.zero_grad()
         numPointsPerTensor = quantization.help_functions.assign_bits_automatically(norms, numPointsPerTensor,
                                                                                    input_is_point=True)

@@ -102,11 +102,11 @@ class ScalingFunction(object):
         rows, row_len, padded = N.geometry(n, _bucket_arg(self.bucket_size))
         dev = x.device
         stat_shape = (rows, 1) if self.bucket_size is not None else (1,)
-        self.alpha = torch.empty(stat_shape, dtype=torch.float32, device=dev)
-        self.beta = torch.empty(stat_shape, dtype=torch.float32, device=dev)
+        ab = torch.empty((2,) + stat_shape, dtype=torch.float32, device=dev)       # one allocation for alpha and beta
+        self.alpha, self.beta = ab[0], ab[1]
         if want_arg:
-            self.idx_min_rows = torch.empty(stat_shape, dtype=torch.int64, device=dev)
-            self.idx_max_rows = torch.empty(stat_shape, dtype=torch.int64, device=dev)
+            mm = torch.empty((2,) + stat_shape, dtype=torch.int64, device=dev)
+            self.idx_min_rows, self.idx_max_rows = mm[0], mm[1]
         self.original_tensor_length = n
         self.expected_tensor_size = torch.Size((rows, row_len)) if self.bucket_size is not None else torch.Size((n,))
         self._mean_dev = _mean_tensor(x, self.subtract_mean)
@@ -173,6 +173,8 @@ def uniformQuantization(tensor, s, type_of_scaling="linear", stochastic_rounding
     Returns ``(quantized tensor, ScalingFunction)``.  One fused kernel: bucket
     min/max, scale, round, de-scale -- 8 bytes of HBM traffic per element."""
     _check_tensor(tensor)
+    if modify_in_place and not tensor.is_contiguous():
+        raise ValueError("modify_in_place needs a contiguous tensor (the reference's .view(-1) has the same requirement)")
     scaling_function = ScalingFunction(type_of_scaling, max_element, subtract_mean, bucket_size, modify_in_place=True)
     was_cpu = not tensor.is_cuda
     x = _to_device(tensor)

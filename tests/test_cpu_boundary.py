@@ -36,8 +36,11 @@ def test_geometry_matches_oracle_without_gpu():
     for n in (1, 10, 255, 256, 257, 1000, 4099, 1 << 26):
         for b in (None, 1, 7, 256, 1024, 100000):
             assert N.geometry(n, 0 if b is None else b) == O.bucket_geometry(n, b)
+            assert N.geometry_native(n, 0 if b is None else b) == O.bucket_geometry(n, b)   # C ABI agrees too
     with pytest.raises(ValueError):
         N.geometry(0, 256)
+    with pytest.raises(ValueError):
+        N.geometry_native(0, 256)
     assert N.lib().qd_workspace_bytes(1 << 34, 0) >= N.lib().qd_workspace_bytes(1 << 20, 256) > 0
 
 

@@ -1,0 +1,10 @@
+import cProfile, pstats, sys, io, torch
+sys.path.insert(0, ".")
+import quantized_distillation_b200.quantization as Q
+x = torch.randn(5000, device="cuda")
+for _ in range(100): Q.uniformQuantization(x, 16, bucket_size=256, modify_in_place=True)
+torch.cuda.synchronize()
+pr = cProfile.Profile(); pr.enable()
+for _ in range(3000): Q.uniformQuantization(x, 16, bucket_size=256, modify_in_place=True)
+pr.disable(); torch.cuda.synchronize()
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18); print(s.getvalue()[:3500])
