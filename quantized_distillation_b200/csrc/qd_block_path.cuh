@@ -323,8 +323,12 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                 s_row, src, len, gvec, pre, mean, max_el,
                 [&](int e, float4 t) {
                     float lv[4];
-                    float4 qo = make_float4(quant(t.x, base + e, lv[0]), quant(t.y, base + e + 1, lv[1]),
-                                            quant(t.z, base + e + 2, lv[2]), quant(t.w, base + e + 3, lv[3]));
+                    float4 qo;
+                    if (P.stochastic)
+                        qo = make_float4(quant(t.x, base + e, lv[0]), quant(t.y, base + e + 1, lv[1]),
+                                         quant(t.z, base + e + 2, lv[2]), quant(t.w, base + e + 3, lv[3]));
+                    else
+                        qo = uniform_quantize_auto4(t, rs.alpha, rs.beta, uf, P.S, P.rS, P.half_minus_band, lv);
                     if (pre) { qo.x = __fadd_rn(qo.x, mean); qo.y = __fadd_rn(qo.y, mean); qo.z = __fadd_rn(qo.z, mean); qo.w = __fadd_rn(qo.w, mean); }
                     if constexpr (BWD != BWD_OFF) {
                         float4 gv = ovec ? *reinterpret_cast<const float4*>(P.g + base + e)

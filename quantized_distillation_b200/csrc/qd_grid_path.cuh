@@ -184,12 +184,8 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
 #pragma unroll
                     for (int u = 0; u < kPer; ++u) {
                         const int e = (it * kPer + u) * (kGridCtaThreads * 4) + threadIdx.x * 4;
-                        float lvl;
-                        float4 qo;
-                        qo.x = uniform_quantize_auto(xv4[u].x, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
-                        qo.y = uniform_quantize_auto(xv4[u].y, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
-                        qo.z = uniform_quantize_auto(xv4[u].z, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
-                        qo.w = uniform_quantize_auto(xv4[u].w, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+                        float lv4[4];
+                        const float4 qo = uniform_quantize_auto4(xv4[u], rs.alpha, rs.beta, uf, P.S, P.rS, P.half_minus_band, lv4);
                         if (P.q != nullptr) st_stream4(P.q + g0 + e, qo);
                         if constexpr (BWD != BWD_OFF) {
                             if constexpr (BWD == BWD_TRUNC) {

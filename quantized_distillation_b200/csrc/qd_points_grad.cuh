@@ -9,8 +9,8 @@
 // bins[k][lane] so that a warp's 32 read-modify-writes always hit 32 distinct
 // banks whatever the indices are.  Per element that is one LDS, one FADD and
 // one STS, independent of K (K <= 32 per sweep; larger K re-sweeps the data).
-// Columns are flushed to float64 every 64 tiles, so float32 only ever adds a
-// few thousand terms; the float64 reduction order is fixed (lane tree -> warps
+// Columns are flushed to float64 every 16 tiles, so float32 only ever adds a
+// few hundred terms; the float64 reduction order is fixed (lane tree -> warps
 // in order -> CTAs in order): the result is deterministic, which keeps
 // data-parallel replicas bit-identical without communication.
 #pragma once
@@ -22,7 +22,7 @@ constexpr int kPgThreads = 256;
 constexpr int kPgWarps = kPgThreads / 32;
 constexpr int kPgTile = 1024;      // elements per warp work item
 constexpr int kPgSweep = 32;       // centroids handled per sweep over the data
-constexpr int kPgFlushEvery = 64;  // tiles between float32 -> float64 flushes
+constexpr int kPgFlushEvery = 16;  // tiles between float32 -> float64 flushes (<= 512 float32 adds per column)
 
 template <typename IdxT>
 __global__ void __launch_bounds__(kPgThreads) points_grad_partial(const float* __restrict__ g,

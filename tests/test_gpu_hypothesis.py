@@ -50,7 +50,7 @@ def test_uniform_forward_random(Q, n, bucket, s, scale, seed, kind, offset):
     assert np.array_equal(sf.idx_max_rows.view(-1).cpu().numpy(), stc["argmax"])
 
 
-@settings(max_examples=80, deadline=None)
+@settings(max_examples=250, deadline=None)
 @given(n=st.integers(1, 120000), bucket=buckets, K=st.integers(1, 64), seed=st.integers(0, 2 ** 20), kind=st.integers(0, 2),
        rule=st.sampled_from(["nearest", "midpoint"]))
 def test_nonuniform_forward_and_points_gradient_random(Q, n, bucket, K, seed, kind, rule):
@@ -70,10 +70,14 @@ def test_nonuniform_forward_and_points_gradient_random(Q, n, bucket, K, seed, ki
         g = rng.standard_normal(n).astype(np.float32)
         _, gp = f.backward(torch.from_numpy(g).cuda())
         ref = CO.nonuniform_bwd_points(g, idxc, stc["alpha"], K, bucket)
-        assert np.abs(gp.cpu().numpy().astype(np.float64) - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30) + 1e-30
-    assert np.array_equal(idx.view(-1).cpu().numpy(), idxc), (n, bucket, K, rule)
-    assert np.array_equal(q.view(-1).cpu().numpy().view(np.uint32), qc.view(np.uint32))
-    assert np.array_equal(alpha.view(-1).cpu().numpy().view(np.uint32), stc["alpha"].view(np.uint32))
+        # tolerance relative to the sum of magnitudes (the per-centroid sums cancel heavily for random g)
+        rows_, row_len_, _ = __import__("oracle.quant_oracle", fromlist=["x"]).bucket_geometry(n, bucket)
+        mag = float(np.abs(g.astype(np.float64) * np.repeat(stc["alpha"].astype(np.float64), row_len_)[:n]).sum())
+        err = np.abs(gp.cpu().numpy().astype(np.float64) - ref).max()
+        assert err <= 1e-6 * mag + 1e-30, ("centroid gradient", n, bucket, K, err, mag)
+    assert np.array_equal(idx.view(-1).cpu().numpy(), idxc), ("idx", n, bucket, K, rule, seed, kind)
+    assert np.array_equal(q.view(-1).cpu().numpy().view(np.uint32), qc.view(np.uint32)), ("q", n, bucket, K, rule, seed, kind)
+    assert np.array_equal(alpha.view(-1).cpu().numpy().view(np.uint32), stc["alpha"].view(np.uint32)), ("alpha", n, bucket, K)
 
 
 @settings(max_examples=60, deadline=None)
