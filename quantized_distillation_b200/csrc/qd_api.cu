@@ -142,8 +142,17 @@ static int launch_warp(const Params& P, bool vec, cudaStream_t s) {
     const int64_t L = P.geo.row_len;
     if (L <= 256) return vec ? launch_warp_inst<OP, BWD, 2, true>(P, s) : launch_warp_inst<OP, BWD, 2, false>(P, s);
     if (L <= 512) return vec ? launch_warp_inst<OP, BWD, 4, true>(P, s) : launch_warp_inst<OP, BWD, 4, false>(P, s);
+    if constexpr (OP == OP_UNIFORM && BWD == (int)BWD_OFF) {
+        // the plain forward also keeps 2048-element rows in registers (64 floats per lane, one CTA per SM):
+        // the two-pass variant for these rows re-reads from DRAM (see qd_block_path.cuh)
+        if (L > 1024) return launch_warp_inst<OP, BWD, 16, true>(P, s);
+    }
     return vec ? launch_warp_inst<OP, BWD, 8, true>(P, s) : launch_warp_inst<OP, BWD, 8, false>(P, s);
 }
+
+// longest row the register-resident warp path takes for (OP, BWD) when rows are 16-byte aligned
+template <int OP, int BWD>
+static constexpr int64_t warp_path_max_row() { return (OP == OP_UNIFORM && BWD == (int)BWD_OFF) ? 2048 : 1024; }
 
 template <int OP, int BWD, bool STAGED, int GROUP>
 static int launch_block_inst(const Params& P, cudaStream_t s) {
@@ -213,7 +222,8 @@ static bool rows_vectorizable(const Params& P) {
 template <int OP, int BWD>
 static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
     if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
-    if (P.geo.row_len <= 1024) return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
+    if (P.geo.row_len <= 1024 || (P.geo.row_len <= warp_path_max_row<OP, BWD>() && rows_vectorizable(P)))
+        return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
     // the CTA / grid paths keep stochastic rounding as a run-time branch of OP_UNIFORM
     constexpr int OP2 = (OP == OP_UNIFORM_STOCH) ? OP_UNIFORM : OP;
     if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP2, BWD>(P, s);
