@@ -85,11 +85,11 @@ __device__ __forceinline__ double cta_sum(double v, double* scratch) {
     return warp_sum(r);  // fixed tree: deterministic
 }
 
-// Measured on B200 (tools/block_bench.py, 64 Mi floats): warp-per-row two-pass wins up to 4096
-// floats per row, the TMA-staged CTA from 8192 up to the 49152-float shared-memory limit; the
+// Measured on B200 (tools/block_bench.py, 64 Mi floats): warp-per-row two-pass wins up to 2048
+// floats per row, the TMA-staged CTA above that, up to the 49152-float shared-memory limit; the
 // CTA-wide L2 re-read variant is kept for completeness (QD_STAGED_MAX can select it).
 constexpr int kStagedMaxRow = QD_MAX_STAGED_BUCKET;  // floats; longer rows would use the L2 re-read variant
-constexpr int kWarpTwoPassMaxRow = 4096;  // floats; rows up to here: one WARP per row, two passes (second from L1/L2)
+constexpr int kWarpTwoPassMaxRow = 2048;  // floats; rows up to here: one WARP per row, two passes (second from L1/L2)
 
 // GROUP = 32: a warp owns the row (no block barriers at all, dozens of rows in flight per SM);
 // GROUP = kBlockCtaThreads: the whole CTA owns the row.
