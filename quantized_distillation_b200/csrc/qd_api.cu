@@ -181,7 +181,9 @@ static int64_t env_threshold(const char* name, int64_t dflt) {
 
 template <int OP, int BWD>
 static int launch_block(const Params& P, cudaStream_t s) {
-    static const int64_t warp2_max = env_threshold("QD_WARP2_MAX", kWarpTwoPassMaxRow);
+    // with the L2 evict_last / evict_first hints the two-pass variant also wins at 4096 for the
+    // single-sweep ops; the min/max backward (three sweeps) is better staged from 2049 on
+    static const int64_t warp2_max = env_threshold("QD_WARP2_MAX", BWD == (int)BWD_MINMAX ? kWarpTwoPassMaxRow : 2 * kWarpTwoPassMaxRow);
     static const int64_t staged_max = env_threshold("QD_STAGED_MAX", kStagedMaxRow);
     if (P.geo.row_len <= warp2_max) return launch_block_inst<OP, BWD, false, 32>(P, s);               // warp per row, two passes
     if (P.geo.row_len <= staged_max) return launch_block_inst<OP, BWD, true, kBlockCtaThreads>(P, s);  // CTA per row, TMA-staged

@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
     const float mean = P.mean ? *P.mean : 0.f;
     const float max_el = P.max_element;
     uint32_t phase_bits = 0;  // bit c = parity the next wait on s_bar[c] must see
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    (void)pol_keep;
     constexpr int kGroups = kBlockCtaThreads / GROUP;  // rows in flight per CTA
 
     for (int64_t row = (int64_t)blockIdx.x * kGroups + (GROUP == 32 ? (threadIdx.x >> 5) : 0); row < P.geo.rows;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
             const int len4 = gvec ? (len & ~3) : 0;
 #pragma unroll 4
             for (int e = tid * 4; e < len4; e += GROUP * 4) {
-                float4 t = ld_stream4(src + e);
+                float4 t = ld_hint4(src + e, pol_keep);          // keep the row in L2 for the passes below
                 if (pre) {
                     t.x = pre_op(t.x, mean, max_el); t.y = pre_op(t.y, mean, max_el);
                     t.z = pre_op(t.z, mean, max_el); t.w = pre_op(t.w, mean, max_el);
@@ -334,11 +336,11 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                         float4 gv = ovec ? *reinterpret_cast<const float4*>(P.g + base + e)
                                          : make_float4(P.g[base + e], P.g[base + e + 1], P.g[base + e + 2], P.g[base + e + 3]);
                         gv.x = fix(e, t.x, gv.x); gv.y = fix(e + 1, t.y, gv.y); gv.z = fix(e + 2, t.z, gv.z); gv.w = fix(e + 3, t.w, gv.w);
-                        if (ovec) st_stream4(P.gout + base + e, gv);
+                        if (ovec) st_hint4(P.gout + base + e, gv, pol_stream);
                         else { P.gout[base + e] = gv.x; P.gout[base + e + 1] = gv.y; P.gout[base + e + 2] = gv.z; P.gout[base + e + 3] = gv.w; }
                     }
                     if (P.q != nullptr) {
-                        if (ovec) st_stream4(P.q + base + e, qo);
+                        if (ovec) st_hint4(P.q + base + e, qo, pol_stream);
                         else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
                     }
                     if (P.idx8 != nullptr) {
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                     float4 qo;
                     const int i0 = one(e, t.x, qo.x), i1 = one(e + 1, t.y, qo.y), i2 = one(e + 2, t.z, qo.z), i3 = one(e + 3, t.w, qo.w);
                     if (P.q != nullptr) {
-                        if (ovec) st_stream4(P.q + base + e, qo);
+                        if (ovec) st_hint4(P.q + base + e, qo, pol_stream);
                         else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
                     }
                     if (P.idx8 != nullptr) {

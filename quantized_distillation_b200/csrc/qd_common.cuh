@@ -104,6 +104,32 @@ __device__ __forceinline__ void st_stream1(float* p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// L2 residency control for the two-pass variants: the first pass tags the row evict_last so that
+// it survives until the second pass, everything streamed once (outputs, the second read) is
+// tagged evict_first (createpolicy + .L2::cache_hint, the mechanism TMA cache hints use).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_hint4(const float* p, uint64_t policy) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void st_hint4(float* p, float4 v, uint64_t policy) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w), "l"(policy)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- Philox4x32-10
 // Counter-based generator for stochastic rounding (quant_functions.py:174-187).
 struct Philox {
