@@ -16,6 +16,7 @@ namespace qd {
 
 constexpr int kGridCtaThreads = 512;
 constexpr int kGridChunk = 16384;  // elements per CTA work item
+constexpr int64_t kGridKeepBytes = 80ll << 20;  // tail of the tensor pinned in the 126 MB L2 between the two passes
 
 struct ChunkPartial {
     float mn, mx;
@@ -34,6 +35,9 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_stats_partial(const __gr
     const bool pre = (P.mean != nullptr) || (P.max_element > 0.f);
     const float mean = P.mean ? *P.mean : 0.f;
     const int64_t items = P.geo.rows * chunks_per_row;
+    // the apply pass walks the tensor backwards: pin the last kGridKeepBytes of it in L2 (evict_last),
+    // let the rest stream through (evict_first), so that the first part of pass 2 is served by L2
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
         const int64_t row = item / chunks_per_row, chunk = item % chunks_per_row;
         const int64_t row_base = row * P.geo.row_len;
@@ -41,11 +45,12 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_stats_partial(const __gr
         const int64_t off = chunk * kGridChunk;
         const int len = (int)min((int64_t)kGridChunk, row_end - off);
         const float* src = P.x + row_base + off;
+        const uint64_t pol = ((P.geo.n - (row_base + off)) * (int64_t)sizeof(float) <= kGridKeepBytes) ? pol_keep : pol_stream;
         float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
         const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
         const int vlen = vec ? (len & ~3) : 0;
         for (int e = threadIdx.x * 4; e < vlen; e += kGridCtaThreads * 4) {
-            float4 t = ld_stream4(src + e);
+            float4 t = ld_hint4(src + e, pol);
             if (pre) {
                 t.x = pre_op(t.x, mean, P.max_element); t.y = pre_op(t.y, mean, P.max_element);
                 t.z = pre_op(t.z, mean, P.max_element); t.w = pre_op(t.w, mean, P.max_element);
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
     const bool pre = (P.mean != nullptr) || (P.max_element > 0.f);
     const float mean = P.mean ? *P.mean : 0.f;
     const int64_t items = P.geo.rows * chunks_per_row;
+    const uint64_t pol_stream = l2_policy_evict_first();
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const int64_t item = items - 1 - it;  // reverse: most recently read data first
         const int64_t row = item / chunks_per_row, chunk = item % chunks_per_row;
@@ -178,15 +184,15 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
 #pragma unroll
                     for (int u = 0; u < kPer; ++u) {
                         const int e = (it * kPer + u) * (kGridCtaThreads * 4) + threadIdx.x * 4;
-                        xv4[u] = ld_stream4(P.x + g0 + e);
-                        if constexpr (BWD != BWD_OFF) gv4[u] = ld_stream4(P.g + g0 + e);
+                        xv4[u] = ld_hint4(P.x + g0 + e, pol_stream);
+                        if constexpr (BWD != BWD_OFF) gv4[u] = ld_hint4(P.g + g0 + e, pol_stream);
                     }
 #pragma unroll
                     for (int u = 0; u < kPer; ++u) {
                         const int e = (it * kPer + u) * (kGridCtaThreads * 4) + threadIdx.x * 4;
                         float lv4[4];
                         const float4 qo = uniform_quantize_auto4(xv4[u], rs.alpha, rs.beta, uf, P.S, P.rS, P.half_minus_band, lv4);
-                        if (P.q != nullptr) st_stream4(P.q + g0 + e, qo);
+                        if (P.q != nullptr) st_hint4(P.q + g0 + e, qo, pol_stream);
                         if constexpr (BWD != BWD_OFF) {
                             if constexpr (BWD == BWD_TRUNC) {
                                 gv4[u].x = (fabsf(xv4[u].x) > 1.0f) ? 0.f : gv4[u].x;
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                                 gv4[u].z = (fabsf(xv4[u].z) > 1.0f) ? 0.f : gv4[u].z;
                                 gv4[u].w = (fabsf(xv4[u].w) > 1.0f) ? 0.f : gv4[u].w;
                             }
-                            st_stream4(P.gout + g0 + e, gv4[u]);
+                            st_hint4(P.gout + g0 + e, gv4[u], pol_stream);
                         }
                     }
                 }
