@@ -120,6 +120,51 @@ __global__ void __launch_bounds__(256) grid_stats_final(const __grid_constant__ 
     }
 }
 
+// One complete, 16-byte aligned chunk of the centroid op: four 128-bit loads in flight, exact
+// x_hat through the hoisted reciprocal with ONE slow-path branch per group of four elements.
+template <int T, bool MID>
+__device__ __forceinline__ void nonuniform_chunk(const float* __restrict__ x, float* __restrict__ q, uint8_t* __restrict__ idx8,
+                                                 const Centroids& cen, const RowState& rs, const RowDivider& div,
+                                                 uint64_t pol_stream) {
+    constexpr int kPer = 4;
+    const float thr = div.thr();
+#pragma unroll 1
+    for (int it = 0; it < kGridChunk / (kGridCtaThreads * 4 * kPer); ++it) {
+        float4 xv4[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) xv4[u] = ld_hint4(x + (it * kPer + u) * (kGridCtaThreads * 4) + threadIdx.x * 4, pol_stream);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int e = (it * kPer + u) * (kGridCtaThreads * 4) + threadIdx.x * 4;
+            const float a[4] = {__fsub_rn(xv4[u].x, rs.beta), __fsub_rn(xv4[u].y, rs.beta), __fsub_rn(xv4[u].z, rs.beta),
+                                __fsub_rn(xv4[u].w, rs.beta)};
+            float xh[4];
+            bool unsafe = !div.ok;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                xh[j] = div.fast(a[j]);
+                unsafe = unsafe || div.needs_exact(a[j], thr);
+            }
+            if (unsafe) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xh[j] = RowDivider::slow_div(a[j], rs.alpha);
+            }
+            float qv[4];
+            int id[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float kval;
+                id[j] = smem_index<T, MID>(cen.k, cen.m, cen.K, xh[j], kval);
+                qv[j] = from_unit(kval, rs.alpha, rs.beta);
+            }
+            if (q != nullptr) st_hint4(q + e, make_float4(qv[0], qv[1], qv[2], qv[3]), pol_stream);
+            if (idx8 != nullptr)
+                *reinterpret_cast<uint32_t*>(idx8 + e) =
+                    (uint32_t)id[0] | ((uint32_t)id[1] << 8) | ((uint32_t)id[2] << 16) | ((uint32_t)id[3] << 24);
+        }
+    }
+}
+
 // element-wise pass; BWD_MINMAX is not offered on this path (the reference
 // refuses bucket_size=None for it, quant_functions.py:332-334)
 template <int OP, int BWD>
@@ -203,6 +248,26 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                             st_hint4(P.gout + g0 + e, gv4[u], pol_stream);
                         }
                     }
+                }
+                continue;
+            }
+        }
+        if constexpr (OP == OP_NONUNIFORM) {
+            // same structure for the centroid op: complete aligned chunk, uint8 (or no) indices;
+            // table size class and index rule are resolved once per chunk, not per element
+            if (vec && len == kGridChunk && P.idx64 == nullptr && !pre) {
+                const float* xs = P.x + g0;
+                float* qs = P.q ? P.q + g0 : nullptr;
+                uint8_t* is = P.idx8 ? P.idx8 + g0 : nullptr;
+                if (cen.K <= 4) {
+                    if (mid_rule) nonuniform_chunk<4, true>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                    else nonuniform_chunk<4, false>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                } else if (cen.K <= 16) {
+                    if (mid_rule) nonuniform_chunk<16, true>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                    else nonuniform_chunk<16, false>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                } else {
+                    if (mid_rule) nonuniform_chunk<256, true>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                    else nonuniform_chunk<256, false>(xs, qs, is, cen, rs, rowdiv, pol_stream);
                 }
                 continue;
             }
