@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                 });
         } else if constexpr (OP == OP_NONUNIFORM) {
             const RowDivider div(rs.alpha);
+            const float thr = div.thr();
+            const bool mid_rule = (P.rule == QD_RULE_MIDPOINT);
             auto one = [&](int e, float t, float& qv) -> int {
                 const float xh = div.exact(__fsub_rn(t, rs.beta));
                 float kval;
@@ -371,8 +373,32 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
             for_each_in_row<STAGED, GROUP>(
                 s_row, src, len, gvec, pre, mean, max_el,
                 [&](int e, float4 t) {
-                    float4 qo;
-                    const int i0 = one(e, t.x, qo.x), i1 = one(e + 1, t.y, qo.y), i2 = one(e + 2, t.z, qo.z), i3 = one(e + 3, t.w, qo.w);
+                    // exact x_hat for four elements with one slow-path branch, then the table search
+                    const float a[4] = {__fsub_rn(t.x, rs.beta), __fsub_rn(t.y, rs.beta), __fsub_rn(t.z, rs.beta), __fsub_rn(t.w, rs.beta)};
+                    float xh[4];
+                    bool unsafe = !div.ok;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        xh[j] = div.fast(a[j]);
+                        unsafe = unsafe || div.needs_exact(a[j], thr);
+                    }
+                    if (unsafe) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xh[j] = RowDivider::slow_div(a[j], rs.alpha);
+                    }
+                    float qq[4];
+                    int ii[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float kval;
+                        if (cen.K <= 4) ii[j] = mid_rule ? smem_index<4, true>(cen.k, cen.m, cen.K, xh[j], kval) : smem_index<4, false>(cen.k, cen.m, cen.K, xh[j], kval);
+                        else if (cen.K <= 16) ii[j] = mid_rule ? smem_index<16, true>(cen.k, cen.m, cen.K, xh[j], kval) : smem_index<16, false>(cen.k, cen.m, cen.K, xh[j], kval);
+                        else ii[j] = mid_rule ? smem_index<256, true>(cen.k, cen.m, cen.K, xh[j], kval) : smem_index<256, false>(cen.k, cen.m, cen.K, xh[j], kval);
+                        qq[j] = from_unit(kval, rs.alpha, rs.beta);
+                        if (pre) qq[j] = __fadd_rn(qq[j], mean);
+                    }
+                    const float4 qo = make_float4(qq[0], qq[1], qq[2], qq[3]);
+                    const int i0 = ii[0], i1 = ii[1], i2 = ii[2], i3 = ii[3];
                     if (P.q != nullptr) {
                         if (ovec) st_hint4(P.q + base + e, qo, pol_stream);
                         else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
