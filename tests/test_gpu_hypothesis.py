@@ -33,7 +33,7 @@ def make(n, scale, seed, kind):
 buckets = st.one_of(st.none(), st.integers(1, 1024), st.integers(1025, 60000))
 
 
-@settings(max_examples=120, deadline=None)
+@settings(max_examples=120, deadline=None, derandomize=True)
 @given(n=st.integers(1, 120000), bucket=buckets, s=st.sampled_from([2, 3, 4, 16, 255, 256, 1000]),
        scale=st.sampled_from([1e-30, 1e-6, 0.05, 1.0, 1e4, 1e30]), seed=st.integers(0, 2 ** 20), kind=st.integers(0, 2),
        offset=st.integers(0, 3))
@@ -50,7 +50,7 @@ def test_uniform_forward_random(Q, n, bucket, s, scale, seed, kind, offset):
     assert np.array_equal(sf.idx_max_rows.view(-1).cpu().numpy(), stc["argmax"])
 
 
-@settings(max_examples=250, deadline=None)
+@settings(max_examples=250, deadline=None, derandomize=True)
 @given(n=st.integers(1, 120000), bucket=buckets, K=st.integers(1, 64), seed=st.integers(0, 2 ** 20), kind=st.integers(0, 2),
        rule=st.sampled_from(["nearest", "midpoint"]))
 def test_nonuniform_forward_and_points_gradient_random(Q, n, bucket, K, seed, kind, rule):
@@ -80,7 +80,7 @@ def test_nonuniform_forward_and_points_gradient_random(Q, n, bucket, K, seed, ki
     assert np.array_equal(alpha.view(-1).cpu().numpy().view(np.uint32), stc["alpha"].view(np.uint32)), ("alpha", n, bucket, K)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(n=st.integers(1, 60000), bucket=st.one_of(st.integers(1, 1024), st.integers(1025, 20000)), s=st.sampled_from([2, 4, 16, 256]),
        seed=st.integers(0, 2 ** 20))
 def test_minmax_backward_random(Q, n, bucket, s, seed):

@@ -27,7 +27,7 @@ def make(n, scale, seed, kind):
     return (x * scale).astype(np.float32)
 
 
-@settings(max_examples=150, deadline=None)
+@settings(max_examples=150, deadline=None, derandomize=True)
 @given(n=sizes, bucket=buckets, s=levels, scale=scales, seed=st.integers(0, 2 ** 20), kind=st.integers(0, 2))
 def test_uniform_three_way_agreement_and_properties(n, bucket, s, scale, seed, kind):
     x = make(n, scale, seed, kind)
@@ -49,7 +49,7 @@ def test_uniform_three_way_agreement_and_properties(n, bucket, s, scale, seed, k
         assert idx[sl][stt["argmin"][r]] == 0
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=100, deadline=None, derandomize=True)
 @given(n=sizes, bucket=buckets, K=st.integers(1, 40), seed=st.integers(0, 2 ** 20), kind=st.integers(0, 2),
        rule=st.sampled_from(["nearest", "midpoint"]))
 def test_nonuniform_three_way_agreement(n, bucket, K, seed, kind, rule):
@@ -72,7 +72,7 @@ def test_nonuniform_three_way_agreement(n, bucket, K, seed, kind, rule):
     assert np.allclose(gp, CO.nonuniform_bwd_points(g, idx, stt["alpha"], K, bucket), rtol=0, atol=1e-12 * max(1.0, np.abs(g * a).sum()))
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(n=st.integers(1, 2000), bucket=st.integers(1, 600), s=st.sampled_from([2, 4, 16, 256]), seed=st.integers(0, 2 ** 20))
 def test_minmax_backward_agreement_and_conservation(n, bucket, s, seed):
     rng = np.random.default_rng(seed)
