@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def built_extension():
+    """The CUDA library is a build artefact (git-ignored): make sure it exists and is not older
+    than its sources before any test imports it.  Building is not a fallback -- if nvcc is missing
+    this raises and the tests fail loudly."""
+    from quantized_distillation_b200 import build as qd_build
+    if qd_build.is_stale():
+        qd_build.build()
+    return qd_build.OUT
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
