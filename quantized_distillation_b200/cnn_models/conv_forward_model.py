@@ -331,14 +331,15 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
             if stop:
                 break
             if mix_with_differentiable_quantization and epoch != start_epoch + epochs_to_train - 1:
-                state = optimize_quantization_points(
+                # the differentiable step works on a copy and hands back its state dict (reference :342-353)
+                quantized_state_dict = optimize_quantization_points(
                     model, train_loader, test_loader, new_learning_rate, initial_momentum=initial_momentum,
                     epochs_to_train=1, print_every=print_every, use_nesterov=use_nesterov,
                     learning_rate_style=learning_rate_style, numPointsPerTensor=2 ** numBits,
                     assignBitsAutomatically=True, bucket_size=bucket_size, use_distillation_loss=True,
                     initialize_method="quantiles", quantize_first_and_last_layer=quantize_first_and_last_layer,
-                    verbose=verbose, evaluate=evaluate)[0]
-                model.load_state_dict(state)
+                    verbose=verbose, evaluate=evaluate, max_steps=max_steps)[0]
+                model.load_state_dict(quantized_state_dict)
                 losses_epochs.append(last_loss_saved)
                 if evaluate:
                     pred_accuracy_epochs.append(cnn_hf.evaluateModel(model, test_loader, fastEvaluation=False))

@@ -56,23 +56,36 @@ def assign_bits_automatically(gradient_norms, inital_bits_to_assign, input_is_po
 
 
 def percentile_plan(n: int, num_points: int, dtype=np.float32):
-    """Which order statistics ``np.percentile(v, linspace(0,100,K))`` reads and
-    with which weights, for ``len(v) == n`` and ``method='linear'``.  Uses
-    numpy's own index arithmetic (numpy/lib/_function_base_impl.py:
-    _QuantileMethods['linear'], _get_indexes, _get_gamma) so the selection is the one
-    numpy makes.  Returns (prev_idx, next_idx, gamma)."""
-    from numpy.lib import _function_base_impl as F
+    """Which order statistics ``np.percentile(v, linspace(0,100,K))`` reads and with which
+    weights, for ``len(v) == n`` and the default ``method='linear'``: virtual index
+    ``(n-1)*q`` in float64 with ``q = linspace(0,100,K) / float32(100)`` (the division numpy
+    makes for a float32 array), previous = floor, next = previous+1, both set to the last
+    element once the virtual index reaches ``n-1``; gamma = virtual - previous.  Restated
+    from the documented algorithm; pinned against ``np.percentile`` itself in
+    tests/test_cpu_boundary.py.  Returns (prev_idx, next_idx, gamma)."""
     q = np.true_divide(np.linspace(0, 100, num=num_points), dtype(100))
-    virt = np.asanyarray(F._QuantileMethods["linear"]["get_virtual_index"](n, q))
-    prev, nxt = F._get_indexes(np.empty(1, dtype=dtype), virt, n)
-    gamma = np.asanyarray(virt - prev, dtype=virt.dtype)
+    virt = (n - 1) * q
+    prev = np.floor(virt).astype(np.intp)
+    nxt = prev + 1
+    above = virt >= n - 1
+    prev[above] = n - 1
+    nxt[above] = n - 1
+    below = virt < 0
+    prev[below] = 0
+    nxt[below] = 0
+    gamma = np.asarray(virt - prev, dtype=virt.dtype)
     return prev, nxt, gamma
 
 
 def percentile_combine(prev_vals: np.ndarray, next_vals: np.ndarray, gamma: np.ndarray) -> np.ndarray:
-    """numpy's linear interpolation of the two neighbours (_lerp)."""
-    from numpy.lib import _function_base_impl as F
-    return np.asarray(F._lerp(prev_vals, next_vals, gamma))
+    """numpy's linear interpolation of the two neighbours: ``a + (b-a)*t``, and
+    ``b - (b-a)*(1-t)`` where ``t >= 0.5`` (float32 difference, float64 product and sum)."""
+    a, b = np.asarray(prev_vals), np.asarray(next_vals)
+    diff = np.subtract(b, a)
+    out = np.asarray(np.add(a, diff * gamma))
+    hi = gamma >= 0.5
+    out[hi] = np.subtract(b, diff * (1 - gamma))[hi]
+    return out
 
 
 def initialize_quantization_points(tensor, scaling_function, num_points):
@@ -88,7 +101,7 @@ def initialize_quantization_points(tensor, scaling_function, num_points):
         scaled = scaled.cuda()
     ordered = torch.sort(scaled)[0]
     prev, nxt, gamma = percentile_plan(n, num_points)
-    sel = torch.from_numpy(np.concatenate([prev % n, nxt % n]).astype(np.int64)).to(ordered.device)
+    sel = torch.from_numpy(np.concatenate([prev, nxt]).astype(np.int64)).to(ordered.device)
     picks = ordered[sel].cpu().numpy()
     initial_points = percentile_combine(picks[:num_points], picks[num_points:], gamma)
     initial_points = torch.from_numpy(np.asarray(initial_points)).type_as(tensor)
@@ -118,6 +131,14 @@ def index_histogram(idx_u8: torch.Tensor, num_bins: int, counts: torch.Tensor = 
         counts = torch.zeros(num_bins, dtype=torch.int64, device=idx_u8.device)
     N.check(N.lib().qd_index_histogram(N.ptr(idx_u8), idx_u8.numel(), num_bins, N.ptr(counts), N.stream_ptr(idx_u8.device)))
     return counts
+
+
+def _add_counts(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    if a.numel() < b.numel():
+        a, b = b, a
+    a = a.clone()
+    a[: b.numel()] += b
+    return a
 
 
 def get_huffman_encoding_mean_bit_length(model_param_iter, quantization_functions, type_quantization="uniform", s=None):
@@ -158,13 +179,21 @@ def get_huffman_encoding_mean_bit_length(model_param_iter, quantization_function
             _, bins, _ = quant_fun(param)
             bins = bins.view(-1)
             nbins = 256
-        bins_u8 = bins.to(torch.uint8)
-        if not bins_u8.is_cuda:
+        if not bins.is_cuda:
             N.require_cuda()
-            bins_u8 = bins_u8.cuda()
+            bins = bins.cuda()
+        if nbins > 256:
+            # more than 8 bits per weight (the reference accepts any s): uint8 codes do not exist,
+            # count the int64 levels with torch instead of the uint8 histogram kernel
+            wide = torch.bincount(bins.view(-1).to(torch.int64), minlength=nbins)
+            counts = wide if counts is None else _add_counts(counts, wide)
+            continue
+        bins_u8 = bins.to(torch.uint8)
         if counts is None:
             counts = torch.zeros(256, dtype=torch.int64, device=bins_u8.device)
-        index_histogram(bins_u8, max(nbins, 1), counts)
+        elif counts.numel() < 256:
+            counts = _add_counts(counts, torch.zeros(256, dtype=torch.int64, device=counts.device))
+        index_histogram(bins_u8, max(nbins, 1), counts[:256])
     counts = counts.cpu().numpy()
     assert total_length == int(counts.sum())                                              # :227
     frequency = defaultdict(int)

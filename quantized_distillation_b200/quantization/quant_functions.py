@@ -244,6 +244,11 @@ class uniformQuantization_variable(object):
             raise NotImplementedError("Right now the code does not work with bucket_size None. Not hard to modify though")
         if self.saved_for_backward is None:                                              # :336-337
             raise ValueError("Need to have called .forward() to be able to call .backward()")
+        if self.maxElementAllowed is not False or self.stochasticRounding:
+            # the reference re-quantizes the saved input with these options inside backward (:341-347);
+            # the backward kernel takes neither, so refuse instead of returning a different gradient
+            raise NotImplementedError("backward with max_element / stochastic_rounding is not implemented "
+                                      "(the reference re-runs the forward with them, quant_functions.py:341-347)")
         _check_tensor(grad_output, "grad_output")
         was_cpu = not grad_output.is_cuda
         x = _to_device(self.saved_for_backward["input"])

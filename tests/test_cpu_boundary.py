@@ -147,9 +147,12 @@ def test_assign_bits_and_huffman_host_logic(golden):
 def test_percentile_plan_is_numpy_percentile():
     from quantized_distillation_b200.quantization import help_functions as H
     rng = np.random.default_rng(0)
-    for n in (1, 2, 3, 10, 255, 1000, 4099):
-        for K in (2, 3, 4, 16, 40):
+    # restated index / interpolation arithmetic (no numpy private imports) == np.percentile, bit for bit
+    for n in (1, 2, 3, 10, 255, 256, 257, 1000, 4099, 100003):
+        for K in (1, 2, 3, 4, 16, 17, 40, 256):
             v = rng.random(n).astype(np.float32)
             o = np.sort(v)
             p, nx, g = H.percentile_plan(n, K)
-            assert np.array_equal(H.percentile_combine(o[p], o[nx], g), np.percentile(v, np.linspace(0, 100, num=K)))
+            ours = np.asarray(H.percentile_combine(o[p], o[nx], g), dtype=np.float64)
+            ref = np.asarray(np.percentile(v, np.linspace(0, 100, num=K)), dtype=np.float64)
+            assert np.array_equal(ours.view(np.uint64), ref.view(np.uint64)), (n, K)
