@@ -40,7 +40,6 @@ LEVELS = 16
 BUCKET = 256
 BYTES_PER_ELEM = 16        # x, g read; q, gout written
 MODE_NAME = "minmax"
-CPU_SAMPLE_ELEMS = 1 << 22
 
 
 def load_peaks():
@@ -156,12 +155,14 @@ def usable_cpus() -> int:
 
 
 _BEST_THREADS = None
+TUNE_ELEMS = 1 << 22       # thread-count tuning sample: 4 Mi elements (16 MB per tensor, larger than any host L2)
 
 
 def best_cpu_threads() -> int:
     """All the host threads the reference's torch ops can USE: torch's intra-op pool is tried at
-    1, 2, 4, ... up to the usable CPU count on a small sample and the fastest setting is kept
-    (on a container whose CPU quota is below the visible core count, more threads is slower)."""
+    1, 2, 4, ... up to the usable CPU count on a 4 Mi-element sample (best of 3 per setting) and
+    the fastest setting is kept -- on a container whose CPU quota is below the visible core
+    count, more threads is slower."""
     global _BEST_THREADS
     if _BEST_THREADS is not None:
         return _BEST_THREADS
@@ -169,13 +170,13 @@ def best_cpu_threads() -> int:
     from oracle import torch_chain as T
     cap = usable_cpus()
     cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, cap) if c <= cap})
-    x = torch.randn(1 << 20) * 0.05
-    g = torch.randn(1 << 20)
+    x = torch.randn(TUNE_ELEMS) * 0.05
+    g = torch.randn(TUNE_ELEMS)
     timing = {}
     for c in cands:
         torch.set_num_threads(c)
         best = float("inf")
-        for _ in range(3):
+        for _ in range(4):
             t0 = time.perf_counter()
             T.uniform_fwd(x, LEVELS, BUCKET)
             T.uniform_bwd_minmax(x, g, LEVELS, BUCKET)
@@ -187,8 +188,9 @@ def best_cpu_threads() -> int:
 
 
 def cpu_port_throughput(n: int, repeats: int, warmup: int):
-    """The reference's CPU path for one fwd+bwd (oracle/torch_chain.py, same torch ops,
-    best thread count on this host).  Returns (GB/s at 16 B/elt, seconds per pass, threads)."""
+    """The reference's CPU path for one fwd+bwd over n elements (oracle/torch_chain.py, same torch
+    ops, best thread count on this host).  Returns (GB/s at 16 B/elt from the MEAN pass time,
+    mean seconds per pass, threads)."""
     import torch
     from oracle import torch_chain as T
     threads = best_cpu_threads()
@@ -196,28 +198,38 @@ def cpu_port_throughput(n: int, repeats: int, warmup: int):
     g0 = torch.Generator().manual_seed(0)
     x = torch.randn(n, generator=g0) * 0.05
     g = torch.randn(n, generator=torch.Generator().manual_seed(1))
-    best = float("inf")
+    total = 0.0
     for i in range(warmup + repeats):
         t0 = time.perf_counter()
         T.uniform_fwd(x, LEVELS, BUCKET)
         T.uniform_bwd_minmax(x, g, LEVELS, BUCKET)
         dt = time.perf_counter() - t0
         if i >= warmup:
-            best = min(best, dt)
-    return n * BYTES_PER_ELEM / best / 1e9, best, threads
+            total += dt
+    mean = total / repeats
+    return n * BYTES_PER_ELEM / mean / 1e9, mean, threads
 
 
 def run_reference_arm(args):
+    """The reference's CPU implementation of the path on the FULL workload: every step is one
+    forward + min/max backward op chain over all 64 Mi elements; `ms_per_step` is the measured
+    mean over the K timed steps (nothing extrapolated)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    gbs, sec, threads = cpu_port_throughput(CPU_SAMPLE_ELEMS, max(1, args.steps), max(1, args.warmup))
-    sample = f"{CPU_SAMPLE_ELEMS} of {N_ELEMS} elements per step (1/16 of the workload), best of {max(1, args.steps)}"
+    n = args.ref_elements or N_ELEMS
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    gbs, sec, threads = cpu_port_throughput(n, steps, warmup)
+    sample = (f"full workload: all {n} elements per step, mean of {steps} timed steps after {warmup} warm-up; "
+              f"thread count tuned on {TUNE_ELEMS} elements") if n == N_ELEMS else \
+             f"REDUCED by --ref-elements: {n} of {N_ELEMS} elements per step (test hook, not a bench value)"
+    cfg = workload_config(args.gpus)
+    cfg["elements"] = n
     print(json.dumps({
         "impl": "reference", "metric": "fake_quant_fused_fwd_bwd_algorithmic_GBps", "value": round(gbs, 3), "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3 * (N_ELEMS / CPU_SAMPLE_ELEMS), 3),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
                          "host_cpus_visible": os.cpu_count(), "host_cpus_usable": usable_cpus()},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -234,32 +246,52 @@ def workload_config(n_gpus):
 
 
 # ----------------------------------------------------------------------------- training legs
-def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False):
+STUDENT_NAME = "ConvolForwardNet smallerModelSpec (22 tensors, 1,000,235 params), teacher teacherModelSpec"
+WRN_NAME = "Wide_ResNet-16-22 student (60 tensors, 82,746,890 params), WRN-28-20 teacher"
+
+
+def build_models(kind, dev):
+    """Random-init student / teacher of BASELINE configs 2-4, built on `dev` (same seed on every rank)."""
+    import torch
+    from quantized_distillation_b200.cnn_models import conv_forward_model as cfm
+    from quantized_distillation_b200.cnn_models.wide_resnet import Wide_ResNet
+    torch.manual_seed(1234)
+    with torch.device(dev):
+        if kind in ("student", "diffquant"):
+            spec = dict(cfm.smallerModelSpec)
+            spec["spec_dropout_rates"] = []
+            student = cfm.ConvolForwardNet(**spec, useBatchNorm=True, useAffineTransformInBatchNorm=True)
+            teacher = cfm.ConvolForwardNet(**cfm.teacherModelSpec, useBatchNorm=True, useAffineTransformInBatchNorm=True).eval()
+        else:
+            student = Wide_ResNet(depth=16, widen_factor=22, dropout_rate=0.3, num_classes=10)
+            teacher = Wide_ResNet(depth=28, widen_factor=20, dropout_rate=0.3, num_classes=10).eval()
+    return student, teacher
+
+
+def leg_settings(kind, world):
+    if kind in ("student", "diffquant"):
+        return dict(per_gpu_batch=25, bits=4, name=STUDENT_NAME,
+                    kw=dict(initial_learning_rate=1e-3, weight_decayL2=2.2e-4))
+    # reference: global batch 100, must divide by the GPU count (cifar10_wideResNet.py:49-51) -> 104 on 8 GPUs
+    per = 100 // world if 100 % world == 0 else 13
+    return dict(per_gpu_batch=per, bits=2, name=WRN_NAME,
+                kw=dict(initial_learning_rate=0.1, weight_decayL2=5e-4, learning_rate_style="cifar100",
+                        quantize_first_and_last_layer=False))
+
+
+def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False, flat=True):
     """CIFAR10-shaped quantized distillation steps/s (BASELINE configs 2-4), synthetic data,
     random-init weights.  Every step copies its batch from pinned host memory and reads the
-    loss back (print_every=1), so the number is end to end.  DDP when world > 1."""
+    loss back (print_every=1), so the number is end to end.  world > 1: FlatDataParallel (one
+    NCCL all-reduce of the flat gradient per step, capturable) or stock DDP (flat=False)."""
     import torch
-    import torch.distributed as dist
     from quantized_distillation_b200 import distributed as D
     from quantized_distillation_b200.cnn_models import conv_forward_model as cfm
     from quantized_distillation_b200.cnn_models import help_fun as hf
-    from quantized_distillation_b200.cnn_models.wide_resnet import Wide_ResNet
 
-    torch.manual_seed(1234)
-    if kind in ("student", "diffquant"):
-        spec = dict(cfm.smallerModelSpec)
-        spec["spec_dropout_rates"] = []
-        student = cfm.ConvolForwardNet(**spec, useBatchNorm=True, useAffineTransformInBatchNorm=True).to(dev)
-        teacher = cfm.ConvolForwardNet(**cfm.teacherModelSpec, useBatchNorm=True, useAffineTransformInBatchNorm=True).to(dev).eval()
-        per_gpu_batch, bits = 25, 4
-        kw = dict(initial_learning_rate=1e-3, weight_decayL2=2.2e-4)
-        name = "ConvolForwardNet smallerModelSpec (22 tensors, 1,000,235 params), teacher teacherModelSpec"
-    else:
-        student = Wide_ResNet(depth=16, widen_factor=22, dropout_rate=0.3, num_classes=10).to(dev)
-        teacher = Wide_ResNet(depth=28, widen_factor=20, dropout_rate=0.3, num_classes=10).to(dev).eval()
-        per_gpu_batch, bits = (100 // world if 100 % world == 0 else 13), 2
-        kw = dict(initial_learning_rate=0.1, weight_decayL2=5e-4, learning_rate_style="cifar100", quantize_first_and_last_layer=False)
-        name = "Wide_ResNet-16-22 student (60 tensors, 82,746,890 params), WRN-28-20 teacher"
+    st = leg_settings(kind, world)
+    student, teacher = build_models(kind, dev)
+    per_gpu_batch, bits = st["per_gpu_batch"], st["bits"]
     total = warmup + steps
     data = hf.synthetic_cifar_loader(total, per_gpu_batch, seed=100 + rank)
     ev = {}
@@ -272,25 +304,156 @@ def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False):
             ev["t1"] = torch.cuda.Event(enable_timing=True)
             ev["t1"].record()
 
+    info = {}
     if kind == "diffquant":
-        cfm.optimize_quantization_points(student, data, data, initial_learning_rate=1e-5, epochs_to_train=1, print_every=1,
-                                         numPointsPerTensor=4, bucket_size=256, use_distillation_loss=True,
-                                         initialize_method="quantiles", verbose=False, evaluate=False, max_steps=total,
-                                         step_hook=hook, cuda_graph_step=graph)
+        info = cfm.optimize_quantization_points(student, data, data, initial_learning_rate=1e-5, epochs_to_train=1, print_every=1,
+                                                numPointsPerTensor=4, bucket_size=256, use_distillation_loss=True,
+                                                initialize_method="quantiles", verbose=False, evaluate=False, max_steps=total,
+                                                step_hook=hook, cuda_graph_step=graph)[2]
         label = "differentiable quantization, 4 centroids per tensor, bucket 256 (BASELINE config 4)"
     else:
-        model = D.wrap_ddp(student, dev)
-        cfm.train_model_quantized(model, data, data, numBits=bits, bucket_size=256, use_distillation_loss=True,
-                                  teacher_model=teacher, epochs_to_train=1, print_every=1, verbose=False, evaluate=False,
-                                  max_steps=total, step_hook=hook, cuda_graph_step=graph, **kw)
+        model = D.wrap_data_parallel(student, dev, flat=flat)
+        info = cfm.train_model_quantized(model, data, data, numBits=bits, bucket_size=256, use_distillation_loss=True,
+                                         teacher_model=teacher, epochs_to_train=1, print_every=1, verbose=False, evaluate=False,
+                                         max_steps=total, step_hook=hook, cuda_graph_step=graph, **st["kw"])[1]
         label = f"{bits}-bit quantized distillation, bucket 256 (BASELINE config {2 if kind == 'student' else 3})"
     torch.cuda.synchronize(dev)
     ms = ev["t0"].elapsed_time(ev["t1"]) / steps
     ms = D.max_over_ranks(ms, dev)
-    return {"config": f"{label}; {name}; per-GPU batch {per_gpu_batch}, global batch {per_gpu_batch * world}, "
-                      f"{'DDP+NCCL' if world > 1 else 'single process'}, synthetic CIFAR-shaped data, loss read back every step",
-            "steps_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 3), "images_per_s": round(per_gpu_batch * world * 1e3 / ms, 1),
-            "steps": steps, "warmup": warmup, "n_gpus": world}
+    par = "single process" if world == 1 else ("FlatDataParallel: 1 NCCL all-reduce of the flat gradient per step" if flat
+                                               else "stock DistributedDataParallel")
+    out = {"config": f"{label}; {st['name']}; per-GPU batch {per_gpu_batch}, global batch {per_gpu_batch * world}, {par}, "
+                     "synthetic CIFAR-shaped data, batch copied from pinned host memory and loss read back every step",
+           "steps_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 3), "images_per_s": round(per_gpu_batch * world * 1e3 / ms, 1),
+           "steps": steps, "warmup": warmup, "n_gpus": world, "cuda_graph_step": bool(graph)}
+    if graph:
+        out["captured"] = bool(info.get("cuda_graph_step", False))
+    del student, teacher
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_style_leg(kind, dev, steps, warmup, threads=None):
+    """The SAME harness driven the way the reference drives it: per step, every selected
+    parameter tensor goes through the reference's stock-torch op chain (oracle/torch_chain.py,
+    bit-identical to the reference on the golden vectors) one tensor at a time, `p.data` is
+    re-bound to the result and re-bound back after the backward pass
+    (cnn_models/conv_forward_model.py:236-247, 286-302; :501-551 for the differentiable loop,
+    pre-processed SearchSorted path incl. its per-step host numpy work).  dev = cuda: what the
+    reference does on a GPU box (USE_CUDA=True).  dev = cpu: its CPU path, model included."""
+    import torch
+    from oracle import torch_chain as T
+    from quantized_distillation_b200.cnn_models import conv_forward_model as cfm
+    from quantized_distillation_b200.cnn_models import help_fun as hf
+    import torch.optim as optim
+
+    on_gpu = dev.type == "cuda"
+    if not on_gpu:
+        torch.set_num_threads(threads or best_cpu_threads())
+    st = leg_settings(kind, 1)
+    student, teacher = build_models(kind, dev)
+    data = hf.synthetic_cifar_loader(warmup + steps, st["per_gpu_batch"], seed=100, pin=on_gpu)
+    levels = 2 ** st["bits"]
+    first_last = st["kw"].get("quantize_first_and_last_layer", True)
+
+    if kind == "diffquant":
+        teacher_net = student.eval()                                       # the unquantized network is the teacher (:497-498)
+        import copy
+        qmodel = copy.deepcopy(student)
+        sel = cfm._selected_parameters(qmodel, True)
+        pres = [T.PreprocessedCentroids(p.data, 256) for p in sel]          # one-time sort per tensor (:501-511)
+        import numpy as np                                                 # percentile initialisation (help_functions.py:140-154)
+        points = [torch.from_numpy(np.percentile(pre.sorted, np.linspace(0, 100, 4)).astype(np.float32)).to(dev)
+                  .requires_grad_(True) for pre in pres]
+        opt = optim.SGD(points, lr=1e-5, momentum=0.9, nesterov=True)
+        qmodel.train()
+
+        def step(batch):
+            qmodel.zero_grad()
+            opt.zero_grad()
+            saved = []
+            for p, pre, pts in zip(sel, pres, points):                     # :525-532
+                q, idx = pre.forward(pts.data)
+                p.data = q
+                saved.append(idx)
+            loss = hf.forward_and_backward(qmodel, batch, 1, 0, use_distillation_loss=True, teacher_model=teacher_net,
+                                           return_tensor=True)
+            for p, pre, pts, idx in zip(sel, pres, points, saved):          # :539-545
+                pts.grad = T.nonuniform_bwd_points(p.grad.data, idx, pre.st, 4, 256)
+            opt.step()
+            for pts in points:                                              # :550-551
+                pts.data = torch.sort(pts.data)[0]
+            return loss
+    else:
+        model = student
+        sel = cfm._selected_parameters(model, first_last)
+        kw = st["kw"]
+        opt = optim.SGD(model.parameters(), lr=kw["initial_learning_rate"], nesterov=True, momentum=0.9,
+                        weight_decay=kw["weight_decayL2"])
+        model.train()
+
+        def step(batch):
+            saved = [p.data for p in sel]                                   # state_dict() keeps the old storages alive (:286)
+            for p in sel:                                                   # :236-247: one op chain per tensor
+                p.data = T.uniform_fwd(p.data, levels, 256)[0]
+            model.zero_grad()
+            loss = hf.forward_and_backward(model, batch, 1, 0, use_distillation_loss=True, teacher_model=teacher,
+                                           return_tensor=True)
+            for p, w in zip(sel, saved):                                    # load_state_dict (:302)
+                p.data = w
+            opt.step()
+            return loss
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize(dev)
+
+    t0 = None
+    for i, batch in enumerate(data):
+        if i == warmup:
+            sync()
+            t0 = time.perf_counter()
+        float(step(batch).item())                                           # loss read back every step, like our leg
+    sync()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    del student, teacher
+    if on_gpu:
+        torch.cuda.empty_cache()
+    return {"steps_per_s": round(1e3 / ms, 3), "ms_per_step": round(ms, 3), "steps": steps, "warmup": warmup,
+            "device": "cuda (stock torch op chain per tensor)" if on_gpu else f"cpu ({torch.get_num_threads()} threads, model included)"}
+
+
+def train_legs(which, world, rank, dev, steps, with_cpu):
+    """BASELINE configs 2/3/4: ours (eager and whole-step CUDA graph) and, at N=1, the
+    reference-style harness timed in the same run."""
+    import torch
+    legs = {}
+    for kind in which:
+        wsteps = steps if kind != "wrn" else max(10, steps // 2)
+        leg = {"eager": run_train_leg(kind, world, rank, dev, wsteps, 8, graph=False)}
+        leg["cuda_graph_step"] = run_train_leg(kind, world, rank, dev, wsteps, 8, graph=True)
+        best = max((leg["eager"], leg["cuda_graph_step"]), key=lambda r: r["steps_per_s"])
+        leg["steps_per_s"], leg["images_per_s"], leg["ms_per_step"] = best["steps_per_s"], best["images_per_s"], best["ms_per_step"]
+        if world == 1 and rank == 0:
+            leg["reference_style_gpu"] = reference_style_leg(kind, dev, max(6, wsteps // 2), 3)
+            leg["reference_style_steps_per_s"] = leg["reference_style_gpu"]["steps_per_s"]
+            leg["speedup_vs_reference_style_gpu"] = round(leg["steps_per_s"] / leg["reference_style_gpu"]["steps_per_s"], 2)
+            if with_cpu and kind != "wrn":
+                leg["reference_style_cpu"] = reference_style_leg(kind, torch.device("cpu"), 3, 1)
+            elif with_cpu:
+                leg["reference_style_cpu"] = {"skipped": "WRN-16-22 + WRN-28-20 teacher at batch 100 on the host cores is minutes per step; "
+                                                         "the per-step quantization alone is in cpu_reference_quantize_ms_per_step"}
+                leg["cpu_reference_quantize_ms_per_step"] = round(cpu_model_quant_ms(WRN_SIZES(), 4, 256, repeats=1), 1)
+        legs[kind] = leg
+    return legs
+
+
+def WRN_SIZES():
+    from quantized_distillation_b200.cnn_models.wide_resnet import Wide_ResNet
+    import torch
+    with torch.device("meta"):
+        m = Wide_ResNet(depth=16, widen_factor=22, dropout_rate=0.3, num_classes=10)
+    return [p.numel() for p in m.parameters()][1:-1]
 
 
 def cpu_model_quant_ms(sizes, levels, bucket, repeats=3):
@@ -318,9 +481,12 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="also print the per-size / per-op table (profiles/)")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--train", default="student", choices=["none", "student", "wrn", "diffquant"],
-                    help="also report CIFAR10-shaped quantized-distillation steps/s (BASELINE configs 2/3/4)")
+    ap.add_argument("--train", default="auto", choices=["auto", "none", "student", "wrn", "diffquant", "all"],
+                    help="CIFAR10-shaped quantized-distillation steps/s (BASELINE configs 2/3/4); auto = student at every N, "
+                         "WRN-16-22 at N=1 and N=8, differentiable quantization at N=1")
     ap.add_argument("--train-steps", type=int, default=40)
+    ap.add_argument("--ref-elements", type=int, default=0,
+                    help="TEST HOOK for --impl reference: run the CPU arm on fewer elements (the line says so; not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -425,7 +591,7 @@ def main():
         "gpu_launches": steps,
         "roofline": {"bound": "hbm", "achieved": round(per_gpu_gbs, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(per_gpu_gbs / peak, 4), "frac_of_nominal_8000": round(per_gpu_gbs / 8000.0, 4),
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": None, "traffic_source": None,
                      "kernel": "qd::warp_rows_kernel<OP_UNIFORM, BWD_MINMAX, R=2, VEC>",
                      "algorithmic_bytes_per_launch": N_ELEMS * BYTES_PER_ELEM},
     }
@@ -433,28 +599,27 @@ def main():
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
-                out["roofline"]["traffic"] = json.load(f).get("uniform_fwd_bwd_minmax_64Mi_dram_bytes")
+                tj = json.load(f)
+            out["roofline"]["traffic"] = tj.get("uniform_fwd_bwd_minmax_64Mi_dram_bytes")
+            out["roofline"]["traffic_source"] = ("profile constant, NOT measured in this run: dram__bytes_read.sum + "
+                                                 "dram__bytes_write.sum of one `ncu --set full` launch, " + str(tj.get("source", "profiles/")))
         except Exception:
             pass
 
     if rank == 0 and world == 1 and not args.no_cpu:
-        gbs, sec, threads = cpu_port_throughput(CPU_SAMPLE_ELEMS, 3, 1)
+        gbs, sec, threads = cpu_port_throughput(N_ELEMS, 3, 1)
         out["cpu_baseline"] = {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port",
-                               "sample": f"{CPU_SAMPLE_ELEMS} of {N_ELEMS} elements (1/16), best of 3, oracle/torch_chain.py "
-                                         "(the reference's torch op chain; /root/reference is absent on the GPU box); "
-                                         "thread count auto-tuned over powers of two up to the usable CPUs",
+                               "sample": f"full workload ({N_ELEMS} elements), mean of 3 passes after 1 warm-up "
+                                         f"({sec * 1e3:.0f} ms per pass), oracle/torch_chain.py (the reference's torch op "
+                                         "chain; /root/reference is absent on the GPU box); thread count tuned over powers "
+                                         f"of two up to the usable CPUs on {TUNE_ELEMS} elements",
                                "host_cpus_visible": os.cpu_count(), "host_cpus_usable": usable_cpus()}
-    if args.train != "none":
-        out["train"] = run_train_leg(args.train, world, rank, dev, args.train_steps, 8)
-        if world == 1:
-            g = run_train_leg(args.train, world, rank, dev, args.train_steps, 8, graph=True)
-            out["train"]["cuda_graph_step"] = {"steps_per_s": g["steps_per_s"], "ms_per_step": g["ms_per_step"],
-                                               "note": "same step, same kernels, captured once in a CUDA graph and replayed "
-                                                       "(train_model(cuda_graph_step=True)); batch H2D copy and loss read-back "
-                                                       "still happen every step"}
-        if rank == 0 and world == 1 and not args.no_cpu and args.train == "student":
-            sizes = [5000, 10, 5625, 75, 93750, 50, 62500, 50, 31250, 25, 800000, 500] + [75, 75, 50, 50, 50, 50, 25, 25, 500, 500]
-            out["train"]["cpu_reference_quantize_ms_per_step"] = round(cpu_model_quant_ms(sizes, 16, 256), 3)
+    which = {"none": [], "student": ["student"], "wrn": ["wrn"], "diffquant": ["diffquant"], "all": ["student", "wrn", "diffquant"],
+             "auto": ["student"] + (["wrn"] if world in (1, 8) else []) + (["diffquant"] if world == 1 else [])}[args.train]
+    if world > 1:
+        which = [k for k in which if k != "diffquant"]           # config 4 is a single-GPU configuration
+    if which:
+        out["train"] = train_legs(which, world, rank, dev, args.train_steps, with_cpu=not args.no_cpu)
     if args.sweep and rank == 0:
         from tools import sweep
         out["sweep_file"] = sweep.run(dev)

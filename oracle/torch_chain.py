@@ -127,6 +127,66 @@ def nonuniform_bwd_points(g: torch.Tensor, idx: torch.Tensor, st: ChainState, nu
     return out
 
 
+class PreprocessedCentroids:
+    """The pre-processed path of the differentiable-quantization loop, pass for pass
+    (quant_functions.py:432-447 preprocess, :509-573 SearchSorted, :275-289 the tail of
+    nonUniformQuantization): the scaled tensor is sorted ONCE on the host; each step costs a
+    K-1 element searchsorted into the sorted copy, one or two N-element index fills in sorted
+    order, a permutation scatter back to tensor order, a host gather of k[idx], the host->device
+    copies of values and int64 indices, and the three-pass inverse scaling on the device."""
+
+    def __init__(self, x: torch.Tensor, bucket):
+        scaled, self.st = scale_down_(x.clone(), bucket)               # :433-437
+        self.device = x.device
+        host = scaled.view(-1).cpu().numpy().copy()                     # :440-445
+        self.order = np.argsort(host)                                   # :520
+        self.sorted = host[self.order]                                  # :521
+        self.rank_of = np.argsort(self.order)                           # :522
+        self.last_runs = None
+        self.last_idx = None
+
+    @staticmethod
+    def _runs(cuts):
+        """(end position in sorted order, centroid index) for every non-empty run (:535-543)."""
+        runs, prev = [], 0
+        for j, c in enumerate(cuts):
+            if c != prev:
+                runs.append((int(c), j))
+                prev = c
+        return runs
+
+    @staticmethod
+    def _fill(runs, n, K):
+        out = np.zeros(n, dtype=int)                                    # :566-573
+        start = 0
+        for end, j in runs:
+            out[start:end] = j
+            start = end
+        out[start:] = K - 1
+        return out
+
+    def query(self, k: np.ndarray) -> np.ndarray:
+        mid = k[:-1] + np.diff(k) / 2                                   # :533
+        runs = self._runs(np.searchsorted(self.sorted, mid))            # :534
+        n, K = self.sorted.shape[0], len(k)
+        if self.last_idx is None:                                       # :545-553
+            self.last_idx = self._fill(runs, n, K)[self.rank_of]
+        else:                                                           # :555-561 incremental update
+            old, new = self._fill(self.last_runs, n, K), self._fill(runs, n, K)
+            moved = new != old
+            self.last_idx[self.order[moved]] = new[moved]
+        self.last_runs = runs
+        return self.last_idx
+
+    def forward(self, points: torch.Tensor):
+        k = points.detach().cpu().numpy()                               # :261
+        idx = self.query(k)
+        vals = torch.from_numpy(k[idx]).to(self.device)                 # :278-284
+        idx_t = torch.from_numpy(idx).long().to(self.device)
+        q = inv_scale_down_(vals.view(*self.st.rows_shape), self.st)    # :286-287
+        return q, idx_t.view(-1)[0:self.st.n].view(self.st.shape)       # :288-289
+
+
 def quantize_model_step(params, s: int, bucket):
     """The per-step choreography of cnn_models/conv_forward_model.py:236-247:
     one uniform_fwd per parameter tensor."""

@@ -108,7 +108,7 @@ class ConvolForwardNet(nn.Module):
 class _GraphedStep:
     """One whole training step captured in a CUDA graph: static input buffers, one replay per step."""
 
-    def __init__(self, step_fn, example_batch, device, stream, optimizer):
+    def __init__(self, step_fn, example_batch, device, stream, optimizer, static_grads=False, collective=False):
         self.ok = False
         try:
             x, y = example_batch
@@ -117,9 +117,14 @@ class _GraphedStep:
             self.x.copy_(x, non_blocking=True)
             self.y.copy_(y, non_blocking=True)
             torch.cuda.synchronize(device)
-            optimizer.zero_grad(set_to_none=True)            # gradients are re-created inside the graph's pool
+            if not static_grads:
+                optimizer.zero_grad(set_to_none=True)        # gradients are re-created inside the graph's pool
+            # (static_grads: they are views of FlatDataParallel's flat buffer, allocated once, address-stable)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=stream):
+            # a captured step that holds an NCCL collective: other threads of the process (the NCCL
+            # watchdog) may touch the CUDA API meanwhile, which only thread-local capture tolerates
+            mode = {"capture_error_mode": "thread_local"} if collective else {}
+            with torch.cuda.graph(self.graph, stream=stream, **mode):
                 self.loss, self.asked, self.total = step_fn((self.x, self.y))
             self.ok = True
         except Exception as e:                               # pragma: no cover - depends on driver / torch build
@@ -253,6 +258,9 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
     epoch = start_epoch
     device = cnn_hf._device_of(model)
     state = {"since": steps_since_estimate}
+    # data parallelism: FlatDataParallel exposes reduce_gradients(); DDP reduces inside backward
+    reduce_gradients = getattr(model, "reduce_gradients", None)
+    flat_dp = reduce_gradients is not None
 
     def one_step(data, idx_minibatch=1, epoch=0):
         """One training step of the reference loop (:280-322) on one batch."""
@@ -263,6 +271,8 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
         loss, c_teach, c_total = cnn_hf.forward_and_backward(
             model, data, idx_minibatch, epoch, use_distillation_loss=use_distillation_loss, teacher_model=teacher_model,
             ask_teacher_strategy=ask_teacher_strategy, return_more_info=True, return_tensor=True)
+        if reduce_gradients is not None:
+            reduce_gradients()                                            # ONE all-reduce of the flat gradient buffer
         if quantize_now:
             quantizer.restore_weights_model()                             # :302
         if add_gradient_noise and not quantizeWeights:
@@ -280,10 +290,11 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
         return loss, c_teach, c_total
 
     strategy_name = (ask_teacher_strategy[0] if isinstance(ask_teacher_strategy, tuple) else ask_teacher_strategy).lower()
+    multi = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+    # stock DDP drives its reducer from autograd hooks on the host and cannot be replayed; the flat
+    # wrapper's single all-reduce can, so a captured step is available for any world size with it
     graph_ok = bool(cuda_graph_step and device.type == "cuda" and estimate_quant_grad_every == 1 and not add_gradient_noise
-                    and strategy_name == "always"
-                    and not (torch.distributed.is_available() and torch.distributed.is_initialized()
-                             and torch.distributed.get_world_size() > 1))
+                    and strategy_name == "always" and (not multi or flat_dp))
     side_stream = torch.cuda.Stream(device) if graph_ok else None
     graphed = None
     try:
@@ -293,8 +304,15 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
             asked, seen = 0, 0
             for idx_minibatch, data in enumerate(train_loader, start=1):
                 if graph_ok and graphed is None and total_steps >= 3:
-                    graphed = _GraphedStep(one_step, data, device, side_stream, optimizer)
-                    if not graphed.ok:
+                    graphed = _GraphedStep(one_step, data, device, side_stream, optimizer, static_grads=flat_dp,
+                                           collective=flat_dp and multi)
+                    captured = graphed.ok
+                    if multi:                                      # replay a collective only if EVERY rank captured it
+                        flag = torch.tensor([1 if captured else 0], dtype=torch.int32, device=device)
+                        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+                        captured = bool(flag.item())
+                    informationDict["cuda_graph_step"] = captured
+                    if not captured:
                         graph_ok, graphed = False, None
                 if graphed is not None and graphed.matches(data):
                     loss, c_teach, c_total = graphed.run(data)
@@ -564,6 +582,7 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
                 graphed = None                                             # the captured update holds the old rate
             group["lr"] = new_learning_rate
     informationDict = {"predictionAccuracy": pred_accuracy_epochs, "numEpochsTrained": epoch + 1,
-                       "lossSaved": losses_epochs, "numStepsTrained": total_steps}
+                       "lossSaved": losses_epochs, "numStepsTrained": total_steps,
+                       "cuda_graph_step": graphed is not None, "cuda_graph_quantization": bool(graphs)}
     # the state dict also carries the batch-norm running statistics of the quantized model (:579-592)
     return quantizedModel.state_dict(), pointsPerTensor, informationDict

@@ -1,5 +1,17 @@
-"""Data-parallel plumbing: one process per GPU, ``DistributedDataParallel`` with NCCL
-gradient all-reduce over NVLink / NVSwitch.
+"""Data-parallel plumbing: one process per GPU, NCCL gradient all-reduce over NVLink /
+NVSwitch.
+
+Two wrappers:
+
+* :class:`FlatDataParallel` (default of ``wrap_data_parallel``) -- every gradient is a view into
+  ONE flat float32 buffer (mirrors ``QuantizationPlan._master_flat``), the step issues ONE
+  all-reduce on it, and nothing in it is host-driven (no reducer hooks, no bucket bookkeeping),
+  so the whole training step -- quantize, forward/backward, all-reduce, restore, gradient
+  fix-up, SGD -- can be captured in one CUDA graph and replayed (NCCL collectives are
+  capturable).  This is what makes the 1 -> 8 GPU curve of the launch-bound student scale.
+* ``wrap_ddp`` -- stock ``DistributedDataParallel`` (bucketed all-reduce overlapped with the
+  backward, eager only); kept for comparison and for models whose backward is long enough to
+  hide the collective.
 
 The reference's multi-GPU story is single-process ``nn.DataParallel``
 (cifar10_wideResNet.py:68-69, 97, 117); the quantization op itself needs no
@@ -46,6 +58,76 @@ def wrap_ddp(model, device):
         return DDP(model, device_ids=[device.index], output_device=device.index, broadcast_buffers=True,
                    gradient_as_bucket_view=True)
     return DDP(model)
+
+
+class FlatDataParallel(torch.nn.Module):
+    """Replicated module whose gradients live in one flat buffer reduced by one collective.
+
+    ``p.grad`` of every trainable parameter is a view of ``flat_grad`` (each tensor starts on a
+    256-byte boundary, so the plan's 128-bit gradient fix-up kernels apply).  Autograd accumulates
+    in place into an existing ``.grad``, ``zero_grad`` is one memset, ``reduce_gradients`` one
+    all-reduce (AVG on NCCL; SUM then scale on gloo).  Parameters and buffers are broadcast from
+    rank 0 once at construction; batch-norm statistics stay replica-local afterwards (the
+    reference's ``nn.DataParallel`` keeps only replica 0's, cifar10_wideResNet.py:68-69)."""
+
+    def __init__(self, module, process_group=None):
+        super().__init__()
+        self.module = module
+        self.process_group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("module has no trainable parameters")
+        if self.world > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, 0, group=process_group)
+        device, dtype = params[0].device, params[0].dtype
+        pad = lambda n: -(-n // 64) * 64                                  # 256-byte granules
+        self.flat_grad = torch.zeros(sum(pad(p.numel()) for p in params), dtype=dtype, device=device)
+        off = 0
+        for p in params:
+            if p.device != device or p.dtype != dtype or not p.is_contiguous():
+                raise ValueError("FlatDataParallel needs contiguous parameters of one dtype on one device")
+            p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+            off += pad(p.numel())
+        self._params = params
+        self._nccl = self.world > 1 and dist.get_backend(process_group) == "nccl"
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def zero_grad(self, set_to_none: bool = False):
+        """One memset; the views stay bound whatever ``set_to_none`` says (a ``None`` gradient
+        would make autograd allocate a fresh tensor outside the flat buffer)."""
+        self.flat_grad.zero_()
+
+    def views_intact(self) -> bool:
+        """True while every ``p.grad`` still aliases the flat buffer (an optimizer's
+        ``zero_grad(set_to_none=True)`` would break that)."""
+        lo = self.flat_grad.data_ptr()
+        hi = lo + self.flat_grad.numel() * self.flat_grad.element_size()
+        return all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self._params)
+
+    def reduce_gradients(self):
+        """Average of the flat gradient over the replicas: ONE collective per step."""
+        if self.world == 1:
+            return
+        if self._nccl:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.process_group)
+        else:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
+            self.flat_grad.mul_(1.0 / self.world)
+
+
+def wrap_data_parallel(model, device=None, flat=True):
+    """Data-parallel wrapper of the training harness: :class:`FlatDataParallel` (graph-capturable,
+    one all-reduce) or stock DDP (``flat=False``).  Single process: the model itself."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return model
+    if flat:
+        return FlatDataParallel(model)
+    return wrap_ddp(model, device if device is not None else next(model.parameters()).device)
 
 
 def shard_batches(batches, rank, world):

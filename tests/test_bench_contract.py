@@ -19,7 +19,9 @@ def run(args, env=None):
 
 
 def test_reference_arm_prints_the_contract_line():
-    res = run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    # --ref-elements is the test hook that shrinks the CPU arm (the driver never passes it: its
+    # run covers all 64 Mi elements per step); the printed line must own up to the reduction
+    res = run(["--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-elements", str(1 << 20)])
     assert res.returncode == 0, res.stderr[-2000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
@@ -30,10 +32,21 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["elements"] == 1 << 20 and "REDUCED" in d["cpu_baseline"]["sample"]
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["ms_per_step"] > 0
+
+
+def test_reference_arm_times_the_full_workload_by_default():
+    """No extrapolation: ms_per_step is the measured mean of K passes over all 64 Mi elements."""
+    import bench
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "n = args.ref_elements or N_ELEMS" in src and bench.N_ELEMS == 1 << 26
+    assert "N_ELEMS / " not in src                                 # the round-1 scale-up of a 1/16 sample is gone
 
 
 def test_reference_arm_other_ranks_exit_quietly():
-    res = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], env={"RANK": "1", "WORLD_SIZE": "2"})
+    res = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--ref-elements", str(1 << 20)],
+              env={"RANK": "1", "WORLD_SIZE": "2"})
     assert res.returncode == 0 and res.stdout.strip() == ""
 
 

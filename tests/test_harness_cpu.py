@@ -125,6 +125,54 @@ def test_ddp_replicas_stay_identical_gloo_world2():
         assert ret[0] is True and ret[1] is True
 
 
+def _student_no_bn():
+    spec = dict(cfm.smallerModelSpec)
+    spec["spec_dropout_rates"] = []
+    return cfm.ConvolForwardNet(**spec, useBatchNorm=False)
+
+
+def _flat_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from quantized_distillation_b200 import distributed as D
+    w, r, device = D.init_distributed(backend="gloo")
+    torch.manual_seed(1234 + r)                                    # DIFFERENT init per rank: the wrapper must broadcast rank 0's
+    model = D.wrap_data_parallel(_student_no_bn(), device)
+    assert isinstance(model, D.FlatDataParallel) and model.views_intact()
+    lo = model.flat_grad.data_ptr()
+    assert all((p.grad.data_ptr() - lo) % 256 == 0 for p in model.parameters())   # 128-bit kernels need aligned rows
+    global_batches = hf.synthetic_cifar_loader(3, 8, seed=7, pin=False)
+    local = D.shard_batches(global_batches, r, w)
+    cfm.train_model(model, local, local, epochs_to_train=1, print_every=1, verbose=False, evaluate=False)
+    assert model.views_intact()                                    # the optimizer never replaced a gradient tensor
+    flat = torch.cat([p.detach().view(-1) for p in model.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(w)]
+    torch.distributed.all_gather(gathered, flat)
+    ret[rank] = bool(torch.equal(gathered[0], gathered[1]))
+    if r == 0:
+        ret["params"] = flat.clone()
+    torch.distributed.destroy_process_group()
+
+
+def test_flat_data_parallel_gloo_world2_matches_single_process():
+    """FlatDataParallel: one flat gradient buffer, one all-reduce per step.  Two gloo ranks on the
+    two halves of each global batch end bit-identical to each other and equal (to float32
+    summation order) to a single process that saw the whole batches with rank 0's start; the model
+    has no batch-norm here, whose statistics are per replica by design."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_flat_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret[0] is True and ret[1] is True
+        dp = ret["params"]
+    torch.manual_seed(1234)
+    single = _student_no_bn()
+    batches = hf.synthetic_cifar_loader(3, 8, seed=7, pin=False)
+    cfm.train_model(single, batches, batches, epochs_to_train=1, print_every=1, verbose=False, evaluate=False)
+    ref = torch.cat([p.detach().view(-1) for p in single.parameters()])
+    assert torch.allclose(dp, ref, atol=2e-6, rtol=1e-4), float((dp - ref).abs().max())
+
+
 def test_state_dict_prefix_helpers():
     from quantized_distillation_b200 import distributed as D
     sd = student().state_dict()
