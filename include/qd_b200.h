@@ -172,6 +172,12 @@ int qd_uniform_fwd_host(const float* x_host, float* q_host, int64_t n, int64_t b
 int qd_uniform_fwd_bwd_host(const float* x_host, const float* g_host, float* q_host, float* gout_host,
                             int64_t n, int64_t bucket, int levels, int mode, int device);
 
+/* ---- benchmark hook: override a path-selection threshold (tools/block_bench.py measures the
+ * variants against each other with it); value -1 restores the built-in choice.
+ *   key 0: longest row (floats) taken by the warp-per-row two-pass variant
+ *   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path */
+int qd_debug_set_tuning(int key, int64_t value);
+
 /* ---- self tests used by tests/ (device side arithmetic checks) ---------- */
 int qd_selftest_division(int64_t pairs, uint64_t seed, int64_t* mismatches, qd_stream_t stream);
 

@@ -46,6 +46,19 @@ def uniform_bwd_minmax(x, g, s, bucket):
     return out
 
 
+def uniform_bwd_minmax_ex(x, g, s, bucket):
+    """(gout, per-row sum |v_j|, per-row r_b): the last two scale the summation-order tolerance."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    g = np.ascontiguousarray(g, dtype=np.float32).reshape(-1)
+    n = x.size
+    rows = 1 if n < bucket else -(-n // bucket)
+    out = np.empty_like(g)
+    ab, r = np.empty(rows, np.float64), np.empty(rows, np.float64)
+    rc = lib().qo_uniform_bwd_minmax_ex(_p(x), _p(g), _p(out), _p(ab), _p(r), C.c_int64(n), C.c_int64(bucket), C.c_int(s))
+    assert rc == 0
+    return out, ab, r
+
+
 def nonuniform_fwd(x, points, bucket, rule="nearest"):
     x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
     pts = np.ascontiguousarray(points, dtype=np.float32)

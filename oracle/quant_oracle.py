@@ -183,6 +183,8 @@ def uniform_bwd_minmax(x, g, s: int, bucket_size):
     owner = np.arange(n) // row_len
     r = np.zeros(rows, dtype=np.float64)
     np.add.at(r, owner, v.astype(np.float64))
+    abs_sum = np.zeros(rows, dtype=np.float64)          # scale of the summation-order tolerance, per bucket
+    np.add.at(abs_sum, owner, np.abs(v.astype(np.float64)))
     base = np.arange(rows, dtype=np.int64) * row_len
     amax = base + st2["argmax"]
     amin = base + st2["argmin"]
@@ -190,7 +192,8 @@ def uniform_bwd_minmax(x, g, s: int, bucket_size):
     np.add.at(corr, amax, r)
     np.add.at(corr, amin, -r)
     out = (gf.astype(np.float64) + corr.astype(F32).astype(np.float64)).astype(F32)
-    return out.reshape(np.shape(g)), dict(r=r, argmax=amax, argmin=amin, alpha2=st2["alpha"], beta2=st2["beta"])
+    return out.reshape(np.shape(g)), dict(r=r, abs_sum=abs_sum, row_len=row_len, argmax=amax, argmin=amin,
+                                          alpha2=st2["alpha"], beta2=st2["beta"])
 
 
 def uniform_bwd_truncated(w, g):

@@ -19,6 +19,7 @@
 #include "qd_grid_path.cuh"
 #include "qd_plan.cuh"
 #include "qd_points_grad.cuh"
+#include "qd_staged_path.cuh"
 #include "qd_warp_path.cuh"
 
 using namespace qd;
@@ -173,21 +174,55 @@ static int launch_block_inst(const Params& P, cudaStream_t s) {
     return QD_OK;
 }
 
-// thresholds between the three variants (floats per row); QD_WARP2_MAX / QD_STAGED_MAX override them for tuning
-static int64_t env_threshold(const char* name, int64_t dflt) {
-    const char* v = getenv(name);
-    return v ? atoll(v) : dflt;
+// ---- tuning hook (benchmarks only): -1 = built-in choice ----------------------------------
+//   key 0: longest row (floats) handled by the warp-per-row two-pass variant of the block path
+//   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path
+static int64_t g_tune[4] = {-1, -1, -1, -1};
+extern "C" int qd_debug_set_tuning(int key, int64_t value) {
+    if (key < 0 || key >= 4) return fail(QD_ERR_INVALID_ARG, "unknown tuning key %d", key);
+    g_tune[key] = value;
+    return QD_OK;
+}
+
+// CTA per row, TMA chunk ring (qd_staged_path.cuh)
+template <int OP, int BWD, int STAGES>
+static int launch_staged_inst(const Params& P, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    auto kern = staged_rows_kernel<OP, BWD, STAGES>;
+    const int stage_floats = (int)((P.geo.row_len + 31) & ~(int64_t)31);
+    const size_t smem = (size_t)STAGES * stage_floats * sizeof(float);
+    if (smem + 8192 > di->smem_optin) return fail(QD_ERR_UNSUPPORTED, "row of %lld floats does not fit in shared memory", (long long)P.geo.row_len);
+    static size_t opted[64] = {};  // largest dynamic size this instantiation was opted into, per device
+    int d = 0;
+    cudaGetDevice(&d);
+    if (smem > opted[d & 63]) {
+        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted[d & 63] = smem;
+    }
+    const int occ = resident_ctas(kern, kBlockCtaThreads, smem);
+    const int64_t cap = (int64_t)di->sms * occ;
+    const int grid = (int)(P.geo.rows < cap ? P.geo.rows : cap);
+    kern<<<grid, kBlockCtaThreads, smem, s>>>(P, stage_floats);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
 }
 
 template <int OP, int BWD>
 static int launch_block(const Params& P, cudaStream_t s) {
-    // with the L2 evict_last / evict_first hints the two-pass variant also wins at 4096 for the
-    // single-sweep ops; the min/max backward (three sweeps) is better staged from 2049 on
-    static const int64_t warp2_max = env_threshold("QD_WARP2_MAX", BWD == (int)BWD_MINMAX ? kWarpTwoPassMaxRow : 2 * kWarpTwoPassMaxRow);
-    static const int64_t staged_max = env_threshold("QD_STAGED_MAX", kStagedMaxRow);
+    // measured on B200 (tools/block_bench.py): see profiles/block_path_r2.txt
+    const int64_t warp2_default = (BWD == (int)BWD_MINMAX) ? kWarpTwoPassMaxRow : 2 * kWarpTwoPassMaxRow;
+    const int64_t warp2_max = g_tune[0] >= 0 ? g_tune[0] : warp2_default;
     if (P.geo.row_len <= warp2_max) return launch_block_inst<OP, BWD, false, 32>(P, s);               // warp per row, two passes
-    if (P.geo.row_len <= staged_max) return launch_block_inst<OP, BWD, true, kBlockCtaThreads>(P, s);  // CTA per row, TMA-staged
-    return launch_block_inst<OP, BWD, false, kBlockCtaThreads>(P, s);                                  // CTA per row, L2 re-read
+    if constexpr (OP == OP_UNIFORM || OP == OP_NONUNIFORM) {
+        if (!P.stochastic) {
+            const int64_t two_max = g_tune[1] >= 0 ? g_tune[1] : kTwoStageMaxRow;
+            if (P.geo.row_len <= two_max && P.geo.row_len <= 24576) return launch_staged_inst<OP, BWD, 2>(P, s);
+            return launch_staged_inst<OP, BWD, 1>(P, s);
+        }
+    }
+    return launch_block_inst<OP, BWD, true, kBlockCtaThreads>(P, s);  // scale / stats / stochastic: CTA per row, whole-row staging
 }
 
 template <int OP, int BWD>
@@ -368,10 +403,11 @@ extern "C" int qd_nonuniform_fwd(const float* x, const float* points, int num_po
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (P.geo.row_len <= 1024) {  // warp path: short centroid tables live in registers (AUX = table size)
         const bool vec = rows_vectorizable(P);
-        if (num_points <= 4) return launch_warp<OP_NONUNIFORM, 4>(P, vec, s);
+        if (num_points <= 4) return launch_warp<OP_NONUNIFORM, 4>(P, vec, s);     // <= 32: table in the lanes (LaneSearch)
         if (num_points <= 8) return launch_warp<OP_NONUNIFORM, 8>(P, vec, s);
-        if (num_points <= 16) return launch_warp<OP_NONUNIFORM, 16>(P, vec, s);   // unrolled search in shared memory
-        if (num_points <= 64) return launch_warp<OP_NONUNIFORM, 64>(P, vec, s);
+        if (num_points <= 16) return launch_warp<OP_NONUNIFORM, 16>(P, vec, s);
+        if (num_points <= 32) return launch_warp<OP_NONUNIFORM, 32>(P, vec, s);
+        if (num_points <= 64) return launch_warp<OP_NONUNIFORM, 64>(P, vec, s);   // unrolled search in shared memory
         return launch_warp<OP_NONUNIFORM, 256>(P, vec, s);
     }
     return run_rows<OP_NONUNIFORM, BWD_OFF>(P, workspace, workspace_bytes, s);
@@ -413,13 +449,13 @@ __global__ void __launch_bounds__(256) centroid_index_kernel(const float* __rest
                                                             int K, int rule, uint8_t* idx8, int64_t* idx64,
                                                             float* unit_out, int64_t n) {
     __shared__ float s_k[256];
-    __shared__ float s_m[256];
-    centroid_setup(s_k, s_m, points, K);
+    __shared__ float s_t[256];
+    centroid_setup(s_k, s_t, points, K, rule);
     __syncthreads();
-    Centroids cen{s_k, s_m, K};
+    Centroids cen{s_k, s_t, K};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int id = centroid_index(cen, xhat[i], rule);
+        const int id = centroid_index(cen, xhat[i]);
         if (idx8) idx8[i] = (uint8_t)id;
         if (idx64) idx64[i] = id;
         if (unit_out) unit_out[i] = s_k[id];

@@ -37,16 +37,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded wait: a bulk copy that never completes (a bad pointer from the caller) must fail the
+// launch with an error, not hang the GPU -- after ~2^26 polls the kernel traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 26)) __trap();
+    }
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -138,11 +144,11 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
     extern __shared__ __align__(128) float s_row[];
     __shared__ __align__(8) uint64_t s_bar[kMaxStageChunks];
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
-    __shared__ float s_m[OP == OP_NONUNIFORM ? 256 : 1];
+    __shared__ float s_t[OP == OP_NONUNIFORM ? 256 : 1];
     __shared__ double s_scratch[kBlockCtaThreads / 32];
 
-    Centroids cen{s_k, s_m, P.num_points};
-    if constexpr (OP == OP_NONUNIFORM) centroid_setup(s_k, s_m, P.points, P.num_points);
+    Centroids cen{s_k, s_t, P.num_points};
+    if constexpr (OP == OP_NONUNIFORM) centroid_setup(s_k, s_t, P.points, P.num_points, P.rule);
     if (STAGED && threadIdx.x == 0) {
         for (int c = 0; c < kMaxStageChunks; ++c) mbar_init(&s_bar[c], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -282,42 +288,27 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                 }
                 return uniform_quantize_auto(xv, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
             };
+            float qlo = 0.f, qhi = 0.f;
+            double acc = 0.0;
+            RowDivider div2(1.0f);
             if constexpr (BWD == BWD_MINMAX) {
-                // second scaling of the quantized row (quant_functions.py:350-363), see the warp path
-                float qmn = __int_as_float(0x7f800000), qmx = __int_as_float(0xff800000);
-                auto q1 = [&](int e, float t) {
-                    float lvl;
-                    const float qv = quant(t, base + e, lvl);
-                    qmn = min_nan(qmn, qv);
-                    qmx = max_nan(qmx, qv);
-                };
-                for_each_in_row<STAGED, GROUP>(s_row, src, len, gvec, pre, mean, max_el,
-                                        [&](int e, float4 t) { q1(e, t.x); q1(e + 1, t.y); q1(e + 2, t.z); q1(e + 3, t.w); }, q1);
-                qmn = grp_minmax<GROUP, true>(qmn, reinterpret_cast<float*>(s_scratch));
-                qmx = grp_minmax<GROUP, false>(qmx, reinterpret_cast<float*>(s_scratch));
-                rs.beta2 = qmn;
-                rs.alpha2 = make_alpha(qmn, qmx);
-                const RowDivider div2(rs.alpha2);
-                double acc = 0.0;
+                // second scaling of the quantized row (quant_functions.py:350-363): q is a monotone function
+                // of x, so min q = Q(min x), max q = Q(max x) exactly (qd_staged_path.cuh) -- no sweep over q
+                float lvl;
+                qlo = quant(mn, 0, lvl);
+                qhi = quant(mx, 0, lvl);
+                rs.beta2 = qlo;
+                rs.alpha2 = make_alpha(qlo, qhi);
+                div2 = RowDivider(rs.alpha2);
                 imin2 = 0x7fffffff; imax2 = 0x7fffffff;
-                auto q2 = [&](int e, float t) {
-                    float lvl;
-                    const float qv = quant(t, base + e, lvl);
-                    if (qv == qmn) imin2 = min(imin2, e);
-                    if (qv == qmx) imax2 = min(imax2, e);
-                    acc += (double)minmax_term(t, qv, P.g[base + e], rs.beta2, div2);
-                };
-                for_each_in_row<STAGED, GROUP>(s_row, src, len, gvec, pre, mean, max_el,
-                                        [&](int e, float4 t) { q2(e, t.x); q2(e + 1, t.y); q2(e + 2, t.z); q2(e + 3, t.w); }, q2);
-                imin2 = grp_min_int<GROUP>(imin2, reinterpret_cast<int*>(s_scratch));
-                imax2 = grp_min_int<GROUP>(imax2, reinterpret_cast<int*>(s_scratch));
-                rb = (float)grp_sum<GROUP>(acc, s_scratch);
             }
-            auto fix = [&](int e, float xv, float gv) -> float {
+            // gout = g here; the two elements the min/max backward changes are patched after the sweep
+            auto fix = [&](int e, float xv, float qv, float gv) -> float {
                 if constexpr (BWD == BWD_TRUNC) gv = (fabsf(xv) > 1.0f) ? 0.f : gv;
-                if (BWD == BWD_MINMAX && imin2 != imax2) {
-                    if (e == imax2) gv = __fadd_rn(gv, rb);
-                    if (e == imin2) gv = __fadd_rn(gv, -rb);
+                if constexpr (BWD == BWD_MINMAX) {
+                    if (qv == qlo) imin2 = min(imin2, e);
+                    if (qv == qhi) imax2 = min(imax2, e);
+                    acc += (double)minmax_term(xv, qv, gv, rs.beta2, div2);
                 }
                 return gv;
             };
@@ -331,15 +322,16 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                                          quant(t.z, base + e + 2, lv[2]), quant(t.w, base + e + 3, lv[3]));
                     else
                         qo = uniform_quantize_auto4(t, rs.alpha, rs.beta, uf, P.S, P.rS, P.half_minus_band, lv);
-                    if (pre) { qo.x = __fadd_rn(qo.x, mean); qo.y = __fadd_rn(qo.y, mean); qo.z = __fadd_rn(qo.z, mean); qo.w = __fadd_rn(qo.w, mean); }
                     if constexpr (BWD != BWD_OFF) {
                         float4 gv = ovec ? *reinterpret_cast<const float4*>(P.g + base + e)
                                          : make_float4(P.g[base + e], P.g[base + e + 1], P.g[base + e + 2], P.g[base + e + 3]);
-                        gv.x = fix(e, t.x, gv.x); gv.y = fix(e + 1, t.y, gv.y); gv.z = fix(e + 2, t.z, gv.z); gv.w = fix(e + 3, t.w, gv.w);
+                        gv.x = fix(e, t.x, qo.x, gv.x); gv.y = fix(e + 1, t.y, qo.y, gv.y);
+                        gv.z = fix(e + 2, t.z, qo.z, gv.z); gv.w = fix(e + 3, t.w, qo.w, gv.w);
                         if (ovec) st_hint4(P.gout + base + e, gv, pol_stream);
                         else { P.gout[base + e] = gv.x; P.gout[base + e + 1] = gv.y; P.gout[base + e + 2] = gv.z; P.gout[base + e + 3] = gv.w; }
                     }
                     if (P.q != nullptr) {
+                        if (pre) { qo.x = __fadd_rn(qo.x, mean); qo.y = __fadd_rn(qo.y, mean); qo.z = __fadd_rn(qo.z, mean); qo.w = __fadd_rn(qo.w, mean); }
                         if (ovec) st_hint4(P.q + base + e, qo, pol_stream);
                         else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
                     }
@@ -352,20 +344,30 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
                 [&](int e, float t) {
                     float lvl;
                     float qv = quant(t, base + e, lvl);
-                    if (pre) qv = __fadd_rn(qv, mean);
-                    if constexpr (BWD != BWD_OFF) P.gout[base + e] = fix(e, t, P.g[base + e]);
-                    if (P.q != nullptr) P.q[base + e] = qv;
+                    if constexpr (BWD != BWD_OFF) P.gout[base + e] = fix(e, t, qv, P.g[base + e]);
+                    if (P.q != nullptr) P.q[base + e] = pre ? __fadd_rn(qv, mean) : qv;
                     if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)(int)lvl;
                 });
+            if constexpr (BWD == BWD_MINMAX) {
+                imin2 = grp_min_int<GROUP>(imin2, reinterpret_cast<int*>(s_scratch));
+                imax2 = grp_min_int<GROUP>(imax2, reinterpret_cast<int*>(s_scratch));
+                rb = (float)grp_sum<GROUP>(acc, s_scratch);
+                if constexpr (GROUP == 32) __syncwarp();   // the row's gout stores are ordered before the patch
+                else __syncthreads();
+                if (tid == 0 && imin2 != imax2) {  // +r at argmax', -r at argmin' (quant_functions.py:380-393)
+                    float* pmax = P.gout + base + imax2;
+                    float* pmin = P.gout + base + imin2;
+                    *pmax = __fadd_rn(__ldcg(pmax), rb);
+                    *pmin = __fadd_rn(__ldcg(pmin), -rb);
+                }
+            }
         } else if constexpr (OP == OP_NONUNIFORM) {
             const RowDivider div(rs.alpha);
             const float thr = div.thr();
-            const bool mid_rule = (P.rule == QD_RULE_MIDPOINT);
             auto one = [&](int e, float t, float& qv) -> int {
                 const float xh = div.exact(__fsub_rn(t, rs.beta));
                 float kval;
-                const int id = (P.rule == QD_RULE_MIDPOINT) ? smem_index<256, true>(cen.k, cen.m, cen.K, xh, kval)
-                                                            : smem_index<256, false>(cen.k, cen.m, cen.K, xh, kval);
+                const int id = smem_index<256>(cen.k, cen.t, xh, kval);
                 qv = from_unit(kval, rs.alpha, rs.beta);
                 if (pre) qv = __fadd_rn(qv, mean);
                 return id;
@@ -391,9 +393,9 @@ __global__ void __launch_bounds__(kBlockCtaThreads) block_rows_kernel(const __gr
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float kval;
-                        if (cen.K <= 4) ii[j] = mid_rule ? smem_index<4, true>(cen.k, cen.m, cen.K, xh[j], kval) : smem_index<4, false>(cen.k, cen.m, cen.K, xh[j], kval);
-                        else if (cen.K <= 16) ii[j] = mid_rule ? smem_index<16, true>(cen.k, cen.m, cen.K, xh[j], kval) : smem_index<16, false>(cen.k, cen.m, cen.K, xh[j], kval);
-                        else ii[j] = mid_rule ? smem_index<256, true>(cen.k, cen.m, cen.K, xh[j], kval) : smem_index<256, false>(cen.k, cen.m, cen.K, xh[j], kval);
+                        if (cen.K <= 4) ii[j] = smem_index<4>(cen.k, cen.t, xh[j], kval);
+                        else if (cen.K <= 16) ii[j] = smem_index<16>(cen.k, cen.t, xh[j], kval);
+                        else ii[j] = smem_index<256>(cen.k, cen.t, xh[j], kval);
                         qq[j] = from_unit(kval, rs.alpha, rs.beta);
                         if (pre) qq[j] = __fadd_rn(qq[j], mean);
                     }

@@ -122,12 +122,22 @@ __global__ void __launch_bounds__(256) grid_stats_final(const __grid_constant__ 
 
 // One complete, 16-byte aligned chunk of the centroid op: four 128-bit loads in flight, exact
 // x_hat through the hoisted reciprocal with ONE slow-path branch per group of four elements.
-template <int T, bool MID>
+// KP <= 32: threshold search and value lookup through the lanes of the warp (LaneSearch; every
+// thread of the CTA runs the same trip count, so the shuffles are warp-uniform); larger tables
+// are searched in shared memory.
+template <int KP>
 __device__ __forceinline__ void nonuniform_chunk(const float* __restrict__ x, float* __restrict__ q, uint8_t* __restrict__ idx8,
                                                  const Centroids& cen, const RowState& rs, const RowDivider& div,
                                                  uint64_t pol_stream) {
     constexpr int kPer = 4;
-    const float thr = div.thr();
+    constexpr bool LANES = KP <= 32;
+    const unsigned thr_bits = __float_as_uint(div.thr()) - 1u;
+    LaneSearch<LANES ? KP : 1> ls;
+    float q_lane = 0.f;
+    if constexpr (LANES) {
+        ls.load(cen, threadIdx.x & 31);
+        q_lane = ls.row_table(rs.alpha, rs.beta, false, 0.f);
+    }
 #pragma unroll 1
     for (int it = 0; it < kGridChunk / (kGridCtaThreads * 4 * kPer); ++it) {
         float4 xv4[kPer];
@@ -139,13 +149,13 @@ __device__ __forceinline__ void nonuniform_chunk(const float* __restrict__ x, fl
             const float a[4] = {__fsub_rn(xv4[u].x, rs.beta), __fsub_rn(xv4[u].y, rs.beta), __fsub_rn(xv4[u].z, rs.beta),
                                 __fsub_rn(xv4[u].w, rs.beta)};
             float xh[4];
-            bool unsafe = !div.ok;
+            unsigned guard = 0xffffffffu;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 xh[j] = div.fast(a[j]);
-                unsafe = unsafe || div.needs_exact(a[j], thr);
+                guard = RowDivider::guard_fold(guard, a[j]);
             }
-            if (unsafe) {
+            if (!div.ok || guard < thr_bits) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) xh[j] = RowDivider::slow_div(a[j], rs.alpha);
             }
@@ -153,9 +163,14 @@ __device__ __forceinline__ void nonuniform_chunk(const float* __restrict__ x, fl
             int id[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float kval;
-                id[j] = smem_index<T, MID>(cen.k, cen.m, cen.K, xh[j], kval);
-                qv[j] = from_unit(kval, rs.alpha, rs.beta);
+                if constexpr (LANES) {
+                    id[j] = ls.index(xh[j]);
+                    qv[j] = LaneSearch<LANES ? KP : 1>::value(q_lane, id[j]);
+                } else {
+                    float kval;
+                    id[j] = smem_index<KP>(cen.k, cen.t, xh[j], kval);
+                    qv[j] = from_unit(kval, rs.alpha, rs.beta);
+                }
             }
             if (q != nullptr) st_hint4(q + e, make_float4(qv[0], qv[1], qv[2], qv[3]), pol_stream);
             if (idx8 != nullptr)
@@ -172,10 +187,10 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                                                              const RowStat* __restrict__ rowstat,
                                                              int64_t chunks_per_row) {
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
-    __shared__ float s_m[OP == OP_NONUNIFORM ? 256 : 1];
-    Centroids cen{s_k, s_m, P.num_points};
+    __shared__ float s_t[OP == OP_NONUNIFORM ? 256 : 1];
+    Centroids cen{s_k, s_t, P.num_points};
     if constexpr (OP == OP_NONUNIFORM) {
-        centroid_setup(s_k, s_m, P.points, P.num_points);
+        centroid_setup(s_k, s_t, P.points, P.num_points, P.rule);
         __syncthreads();
     }
     const bool pre = (P.mean != nullptr) || (P.max_element > 0.f);
@@ -194,7 +209,6 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
         rs.beta = rowstat[row].beta;
         const UniformFast uf = make_uniform_fast(rs.alpha, P.S);
         const RowDivider rowdiv(rs.alpha);
-        const bool mid_rule = (P.rule == QD_RULE_MIDPOINT);
         if constexpr (OP == OP_SCALE) {
             // padded layout: positions past the end of the tail row repeat x_hat of the last element
             const int plen = (int)min((int64_t)kGridChunk, P.geo.row_len - off);
@@ -259,16 +273,12 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                 const float* xs = P.x + g0;
                 float* qs = P.q ? P.q + g0 : nullptr;
                 uint8_t* is = P.idx8 ? P.idx8 + g0 : nullptr;
-                if (cen.K <= 4) {
-                    if (mid_rule) nonuniform_chunk<4, true>(xs, qs, is, cen, rs, rowdiv, pol_stream);
-                    else nonuniform_chunk<4, false>(xs, qs, is, cen, rs, rowdiv, pol_stream);
-                } else if (cen.K <= 16) {
-                    if (mid_rule) nonuniform_chunk<16, true>(xs, qs, is, cen, rs, rowdiv, pol_stream);
-                    else nonuniform_chunk<16, false>(xs, qs, is, cen, rs, rowdiv, pol_stream);
-                } else {
-                    if (mid_rule) nonuniform_chunk<256, true>(xs, qs, is, cen, rs, rowdiv, pol_stream);
-                    else nonuniform_chunk<256, false>(xs, qs, is, cen, rs, rowdiv, pol_stream);
-                }
+                if (cen.K <= 4) nonuniform_chunk<4>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                else if (cen.K <= 8) nonuniform_chunk<8>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                else if (cen.K <= 16) nonuniform_chunk<16>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                else if (cen.K <= 32) nonuniform_chunk<32>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                else if (cen.K <= 64) nonuniform_chunk<64>(xs, qs, is, cen, rs, rowdiv, pol_stream);
+                else nonuniform_chunk<256>(xs, qs, is, cen, rs, rowdiv, pol_stream);
                 continue;
             }
         }
@@ -307,13 +317,9 @@ __global__ void __launch_bounds__(kGridCtaThreads) grid_apply(const __grid_const
                     const float xh = rowdiv.exact(__fsub_rn(t, rs.beta));
                     float kval;
                     int id;
-                    if (cen.K <= 4) {
-                        id = mid_rule ? smem_index<4, true>(cen.k, cen.m, cen.K, xh, kval) : smem_index<4, false>(cen.k, cen.m, cen.K, xh, kval);
-                    } else if (cen.K <= 16) {
-                        id = mid_rule ? smem_index<16, true>(cen.k, cen.m, cen.K, xh, kval) : smem_index<16, false>(cen.k, cen.m, cen.K, xh, kval);
-                    } else {
-                        id = mid_rule ? smem_index<256, true>(cen.k, cen.m, cen.K, xh, kval) : smem_index<256, false>(cen.k, cen.m, cen.K, xh, kval);
-                    }
+                    if (cen.K <= 4) id = smem_index<4>(cen.k, cen.t, xh, kval);
+                    else if (cen.K <= 16) id = smem_index<16>(cen.k, cen.t, xh, kval);
+                    else id = smem_index<256>(cen.k, cen.t, xh, kval);
                     lv[j] = (float)id;
                     qv[j] = from_unit(kval, rs.alpha, rs.beta);
                 }

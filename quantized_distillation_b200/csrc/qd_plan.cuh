@@ -41,7 +41,7 @@ template <int R, bool VEC, bool FULL>
 __device__ __forceinline__ void plan_forward_row(const Params& P, float* save, int64_t row, int lane) {
     float v[4 * R], gv[4 * R];
     Centroids cen{nullptr, nullptr, 0};
-    RegTable<0> rt;
+    LaneTable<OP_UNIFORM, BWD_OFF> rt;
     warp_load_row<OP_UNIFORM, BWD_OFF, R, VEC, FULL>(P, row, lane, v, gv);
     if (save != nullptr) {
         const int64_t base = row * P.geo.row_len;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEn
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
     Centroids cen{nullptr, nullptr, 0};
-    RegTable<0> rt;
+    LaneTable<OP_UNIFORM, BWD_OFF> rt;
     for (int64_t grow = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); grow < total_rows; grow += stride) {
         int lo = 0, hi = count - 1;  // largest t with row_start[t] <= grow
         while (lo < hi) {

@@ -110,8 +110,11 @@ __device__ __forceinline__ void store_row_u8(uint8_t* __restrict__ p, int len, i
     }
 }
 
-// AUX is the backward mode for OP_UNIFORM and the register-table size KR (0 = table in
-// shared memory) for OP_NONUNIFORM.
+// AUX is the backward mode for OP_UNIFORM and the centroid-table size class KP for
+// OP_NONUNIFORM (power of two >= K; <= 32: table in the lanes of the warp, else shared memory).
+template <int OP, int AUX>
+using LaneTable = LaneSearch<(OP == OP_NONUNIFORM && AUX <= 32) ? AUX : 1>;
+
 template <int OP, int AUX, int R, bool VEC, bool FULL>
 __device__ __forceinline__ void warp_load_row(const Params& P, int64_t row, int lane, float (&v)[4 * R], float (&gv)[4 * R]) {
     constexpr int BWD = (OP == OP_UNIFORM) ? AUX : (int)BWD_OFF;
@@ -122,11 +125,10 @@ __device__ __forceinline__ void warp_load_row(const Params& P, int64_t row, int 
 }
 
 template <int OP, int AUX, int R, bool VEC, bool FULL>
-__device__ __forceinline__ void warp_compute_row(const Params& P, const Centroids& cen,
-                                                 const RegTable<(OP == OP_NONUNIFORM && AUX <= 8 ? AUX : 0)>& rt, int64_t row,
+__device__ __forceinline__ void warp_compute_row(const Params& P, const Centroids& cen, const LaneTable<OP, AUX>& rt, int64_t row,
                                                  int lane, float (&v)[4 * R], float (&gv)[4 * R]) {
     constexpr int BWD = (OP == OP_UNIFORM) ? AUX : (int)BWD_OFF;
-    constexpr int KR = (OP == OP_NONUNIFORM) ? AUX : 0;
+    constexpr int KP = (OP == OP_NONUNIFORM) ? AUX : 0;
     constexpr int E = 4 * R;
     const int64_t base = row * P.geo.row_len;
     const int len = FULL ? R * 128 : (int)min(P.geo.row_len, P.geo.n - base);
@@ -317,44 +319,34 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
         // whole row, one warp vote, IEEE routine for the (rare) rows holding an element outside the
         // sequence's proven domain (see RowDivider)
         const RowDivider div(rs.alpha);
-        const float thr = div.thr();
-        Pivot16 pv16;
-        if constexpr (KR == 16) pv16.load(cen);      // six broadcast loads per row, hoisted out of the element loop
         float xh[E];
-        bool unsafe = !div.ok;
+        unsigned guard = 0xffffffffu;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
             const float a = __fsub_rn(v[i], rs.beta);
             xh[i] = div.fast(a);
-            unsafe = unsafe || div.needs_exact(a, thr);
+            guard = RowDivider::guard_fold(guard, a);
         }
-        if (__any_sync(kFullMask, unsafe)) {
+        if (__any_sync(kFullMask, div.guard_unsafe(guard))) {
 #pragma unroll
             for (int i = 0; i < E; ++i) xh[i] = RowDivider::slow_div(__fsub_rn(v[i], rs.beta), rs.alpha);
         }
-        // the rule is uniform for the launch: branch once per row, not once per element
-        if (P.rule == QD_RULE_MIDPOINT) {
+        // either rule is a count of per-launch thresholds (qd_rowops.cuh)
+        if constexpr (KP <= 32) {
+            const float q_lane = rt.row_table(rs.alpha, rs.beta, pre, rs.mean);   // lane L: k_L*alpha + beta (+ mean)
 #pragma unroll
             for (int i = 0; i < E; ++i) {
-                float kval;
-                if constexpr (KR == 16) li[i] = pivot_index16<true>(cen.k, cen.m, pv16, cen.K, xh[i], kval);
-                else if constexpr (KR > 8) li[i] = smem_index<KR, true>(cen.k, cen.m, cen.K, xh[i], kval);
-                else li[i] = rt.template index<true>(xh[i], cen.K, kval);
-                qv[i] = from_unit(kval, rs.alpha, rs.beta);
+                li[i] = rt.index(xh[i]);
+                qv[i] = LaneTable<OP, AUX>::value(q_lane, li[i]);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 float kval;
-                if constexpr (KR == 16) li[i] = pivot_index16<false>(cen.k, cen.m, pv16, cen.K, xh[i], kval);
-                else if constexpr (KR > 8) li[i] = smem_index<KR, false>(cen.k, cen.m, cen.K, xh[i], kval);
-                else li[i] = rt.template index<false>(xh[i], cen.K, kval);
+                li[i] = smem_index<KP>(cen.k, cen.t, xh[i], kval);
                 qv[i] = from_unit(kval, rs.alpha, rs.beta);
+                if (pre) qv[i] = __fadd_rn(qv[i], rs.mean);
             }
-        }
-        if (pre) {
-#pragma unroll
-            for (int i = 0; i < E; ++i) qv[i] = __fadd_rn(qv[i], rs.mean);
         }
         if (P.q != nullptr) store_row<R, VEC, FULL>(P.q + base, len, lane, qv);
         if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, li);
@@ -372,8 +364,7 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
 }
 
 template <int OP, int AUX, int R, bool VEC, bool FULL>
-__device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen,
-                                                 const RegTable<(OP == OP_NONUNIFORM && AUX <= 8 ? AUX : 0)>& rt, int64_t row,
+__device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen, const LaneTable<OP, AUX>& rt, int64_t row,
                                                  int lane) {
     float v[4 * R], gv[4 * R];
     warp_load_row<OP, AUX, R, VEC, FULL>(P, row, lane, v, gv);
@@ -398,16 +389,16 @@ constexpr int kMinCtas = (OP == OP_UNIFORM && R == 2 && (AUX == (int)BWD_OFF || 
 
 template <int OP, int AUX, int R, bool VEC>
 __global__ void __launch_bounds__(kWarpCtaThreads, kMinCtas<OP, AUX, R>) warp_rows_kernel(const __grid_constant__ Params P) {
-    __shared__ __align__(16) float s_k[OP == OP_NONUNIFORM ? 256 : 1];   // 16-byte aligned: read as float4 groups
-    __shared__ __align__(16) float s_m[OP == OP_NONUNIFORM ? 256 : 1];
-    Centroids cen{s_k, s_m, P.num_points};
-    RegTable<(OP == OP_NONUNIFORM && AUX <= 8 ? AUX : 0)> rt;
-    if constexpr (OP == OP_NONUNIFORM) {
-        centroid_setup(s_k, s_m, P.points, P.num_points);
-        __syncthreads();
-        rt.load(cen);
-    }
+    __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
+    __shared__ float s_t[OP == OP_NONUNIFORM ? 256 : 1];
+    Centroids cen{s_k, s_t, P.num_points};
+    LaneTable<OP, AUX> rt;
     const int lane = threadIdx.x & 31;
+    if constexpr (OP == OP_NONUNIFORM) {
+        centroid_setup(s_k, s_t, P.points, P.num_points, P.rule);
+        __syncthreads();
+        if constexpr (AUX <= 32) rt.load(cen, lane);
+    }
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
     int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     // rows [0, full_rows) are complete, 16-byte aligned rows of exactly R*128 elements

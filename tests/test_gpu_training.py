@@ -208,3 +208,28 @@ def test_whole_step_cuda_graph_matches_eager(env, style):
     torch.backends.cudnn.deterministic = False
     for a, b in zip(*finals):
         assert (a != b).float().mean() < 0.02, "more than a few level flips between graph and eager training"
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_mix_with_differentiable_quantization_two_epochs(env, graph):
+    """train_model(mix_with_differentiable_quantization=True): after every epoch but the last the
+    quantization points are optimised for one epoch and the result is loaded back (reference
+    cnn_models/conv_forward_model.py:342-353).  Round 1 crashed on the second epoch (the step-state
+    dict was overwritten by the returned state dict)."""
+    Q, cfm, hf = env
+    torch.manual_seed(5)
+    student = make_student(cfm)
+    teacher = make_student(cfm).eval()
+    data = hf.synthetic_cifar_loader(4, 25, seed=9)
+    before = [p.detach().clone() for p in student.parameters()]
+    model, info = cfm.train_model_quantized(student, data, data, numBits=2, bucket_size=256, use_distillation_loss=True,
+                                            teacher_model=teacher, epochs_to_train=2, print_every=2, verbose=False,
+                                            evaluate=False, mix_with_differentiable_quantization=True, cuda_graph_step=graph)
+    assert info["errorFlag"] is False and info["numStepsTrained"] == 8
+    assert info["numEpochsTrained"] == 4                              # doubled like the reference (:376-377)
+    assert len(info["lossSaved"]) == 3                                # epoch 1, the differentiable epoch, epoch 2
+    params = list(model.parameters())
+    assert any(not torch.equal(a, b) for a, b in zip(before, params))
+    for p in params:                                                   # returned weights are 2-bit quantized per bucket
+        assert distinct_per_bucket(p, 256) <= 4
+        assert torch.isfinite(p).all()

@@ -1,4 +1,11 @@
-"""Throughput of the CTA-per-row (TMA-staged) path for several row lengths."""
+"""Throughput of the block path (rows of 1025 .. 49152 floats) per row length, op and VARIANT:
+warp-per-row two-pass, CTA-per-row TMA chunk ring with two rows in flight (staged2) or one (staged1).
+The variants are forced through qd_debug_set_tuning; `auto` is the built-in choice.
+
+    python tools/block_bench.py [--out gpurun_out/block_path.json] [--quick]
+"""
+import argparse
+import json
 import os
 import sys
 
@@ -8,32 +15,92 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from quantized_distillation_b200 import _native as N  # noqa: E402
 
-dev = torch.device("cuda", 0)
-lib, sp = N.lib(), N.stream_ptr(dev)
-n = 1 << 26
-x = torch.randn(n, device=dev) * 0.05
-g = torch.randn(n, device=dev)
-q, go = torch.empty_like(x), torch.empty_like(g)
-idx = torch.empty(n, dtype=torch.uint8, device=dev)
-pts = torch.linspace(0, 1, 4, device=dev)
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "block_path.json"))
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    lib, sp = N.lib(), N.stream_ptr(dev)
+    peak = 6650.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = float(json.load(open(pk))["hbm_gbs"])
+    n = 1 << 26
+    x = torch.randn(n, device=dev) * 0.05
+    g = torch.randn(n, device=dev)
+    q, go = torch.empty_like(x), torch.empty_like(g)
+    idx = torch.empty(n, dtype=torch.uint8, device=dev)
+    pts4 = torch.linspace(0, 1, 4, device=dev)
+    pts16 = torch.sort(torch.rand(16, device=dev))[0]
+
+    def timed(fn, iters=8):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    def tune(key, value):
+        N.check(lib.qd_debug_set_tuning(key, value))
+
+    rows = []
+    buckets = (2048, 8192, 49152) if args.quick else (1280, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152)
+    for bucket in buckets:
+        ws = N.workspace(n, bucket, dev)
+        ops = {
+            "uniform_fwd": (8, lambda: N.check(lib.qd_uniform_fwd(N.ptr(x), N.ptr(q), None, None, None, None, None, n, bucket, 16, None, 0.0, 0, 0, 0, N.ptr(ws), ws.numel(), sp))),
+            "fused_ste": (16, lambda: N.check(lib.qd_uniform_fwd_bwd(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, bucket, 16, N.BWD_STE, N.ptr(ws), ws.numel(), sp))),
+            "fused_minmax": (16, lambda: N.check(lib.qd_uniform_fwd_bwd(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, bucket, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(), sp))),
+            "bwd_minmax": (12, lambda: N.check(lib.qd_uniform_bwd(N.ptr(x), N.ptr(g), N.ptr(go), n, bucket, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(), sp))),
+            "nonuniform_K4_mid": (9, lambda: N.check(lib.qd_nonuniform_fwd(N.ptr(x), N.ptr(pts4), 4, N.RULE_MIDPOINT, N.ptr(q), N.ptr(idx), None, None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp))),
+            "nonuniform_K16_near": (9, lambda: N.check(lib.qd_nonuniform_fwd(N.ptr(x), N.ptr(pts16), 16, N.RULE_NEAREST, N.ptr(q), N.ptr(idx), None, None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp))),
+        }
+        variants = {"auto": (-1, -1)}
+        if bucket <= 8192:
+            variants["warp2"] = (1 << 20, -1)
+        if bucket <= 24576:
+            variants["staged2"] = (0, 1 << 20)
+        variants["staged1"] = (0, 0)
+        for vname, (t0, t1) in variants.items():
+            tune(0, t0)
+            tune(1, t1)
+            for oname, (bpe, fn) in ops.items():
+                if vname == "warp2" and oname == "uniform_fwd" and bucket <= 2048:
+                    continue          # the plain forward keeps rows <= 2048 in registers (warp path), not a block variant
+                sec = timed(fn)
+                gbs = n * bpe / sec / 1e9
+                rows.append({"bucket": bucket, "variant": vname, "op": oname, "us": round(sec * 1e6, 1), "GBps": round(gbs, 1),
+                             "frac_measured_peak": round(gbs / peak, 3)})
+        tune(0, -1)
+        tune(1, -1)
+        line = f"bucket {bucket:6d}: " + " | ".join(
+            f"{o} " + "/".join(f"{v[:3]}{r['us']:.0f}" for r in rows if r["bucket"] == bucket and r["op"] == o for v in [r["variant"]])
+            for o in ops)
+        print(line, flush=True)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump({"n": n, "peak_GBps": peak, "rows": rows}, f, indent=1)
+    with open(args.out.replace(".json", ".md"), "w") as f:
+        f.write(f"64 Mi float32, levels 16; microseconds per launch (fraction of the measured HBM peak {peak:.0f} GB/s)\n\n")
+        opn = list(dict.fromkeys(r["op"] for r in rows))
+        f.write("| bucket | variant | " + " | ".join(opn) + " |\n|---|---|" + "---|" * len(opn) + "\n")
+        for b in buckets:
+            for v in ("auto", "warp2", "staged2", "staged1"):
+                cells = []
+                for o in opn:
+                    m = [r for r in rows if r["bucket"] == b and r["variant"] == v and r["op"] == o]
+                    cells.append(f"{m[0]['us']:.0f} ({m[0]['frac_measured_peak']:.2f})" if m else "-")
+                if any(c != "-" for c in cells):
+                    f.write(f"| {b} | {v} | " + " | ".join(cells) + " |\n")
+    print("wrote", args.out)
 
 
-def timed(fn, iters=10):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e-3
-
-
-for bucket in (512, 1024, 2048, 4096, 8192, 16384, 32768, 49152):
-    ws = N.workspace(n, bucket, dev)
-    t_f = timed(lambda: N.check(lib.qd_uniform_fwd(N.ptr(x), N.ptr(q), None, None, None, None, None, n, bucket, 16, None, 0.0, 0, 0, 0, N.ptr(ws), ws.numel(), sp)))
-    t_b = timed(lambda: N.check(lib.qd_uniform_fwd_bwd(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, bucket, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(), sp)))
-    t_n = timed(lambda: N.check(lib.qd_nonuniform_fwd(N.ptr(x), N.ptr(pts), 4, N.RULE_MIDPOINT, N.ptr(q), N.ptr(idx), None, None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp)))
-    print(f"bucket {bucket:6d}: uniform fwd {t_f*1e6:8.1f} us {n*8/t_f/1e9:7.0f} GB/s | fused minmax {t_b*1e6:8.1f} us {n*16/t_b/1e9:7.0f} GB/s | nonuniform K4 {t_n*1e6:8.1f} us {n*9/t_n/1e9:7.0f} GB/s")
+if __name__ == "__main__":
+    main()

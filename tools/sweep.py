@@ -57,6 +57,7 @@ def run(dev=None, out_path=None, max_log2=28, min_log2=10):
         idx = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
         pts4 = torch.linspace(0, 1, 4, device=dev)
         pts16 = torch.linspace(0, 1, 16, device=dev)
+        pts8 = torch.linspace(0, 1, 8, device=dev)
         gp = torch.empty(16, device=dev)
         for bucket in (256, 0):
             ws = N.workspace(n, bucket, dev)
@@ -75,6 +76,12 @@ def run(dev=None, out_path=None, max_log2=28, min_log2=10):
                     N.ptr(ws), ws.numel(), sp))),
                 "nonuniform_fwd_K16_nearest_u8": (9 if bucket or n <= 49152 else 13, lambda i: N.check(lib.qd_nonuniform_fwd(
                     N.ptr(xs[i]), N.ptr(pts16), 16, N.RULE_NEAREST, N.ptr(qs[i]), N.ptr(idx[i]), None, None, None, n, bucket, None, 0.0,
+                    N.ptr(ws), ws.numel(), sp))),
+                "nonuniform_fwd_K8_nearest_u8": (9 if bucket or n <= 49152 else 13, lambda i: N.check(lib.qd_nonuniform_fwd(
+                    N.ptr(xs[i]), N.ptr(pts8), 8, N.RULE_NEAREST, N.ptr(qs[i]), N.ptr(idx[i]), None, None, None, n, bucket, None, 0.0,
+                    N.ptr(ws), ws.numel(), sp))),
+                "nonuniform_fwd_K16_midpoint_u8": (9 if bucket or n <= 49152 else 13, lambda i: N.check(lib.qd_nonuniform_fwd(
+                    N.ptr(xs[i]), N.ptr(pts16), 16, N.RULE_MIDPOINT, N.ptr(qs[i]), N.ptr(idx[i]), None, None, None, n, bucket, None, 0.0,
                     N.ptr(ws), ws.numel(), sp))),
                 "nonuniform_bwd_K4_u8": (5, lambda i: N.check(lib.qd_nonuniform_bwd(
                     N.ptr(gs[i]), N.ptr(idx[i]), None, N.ptr(alpha), 4, N.ptr(gp), n, bucket, N.ptr(ws), ws.numel(), sp))),
