@@ -164,6 +164,24 @@ int qd_plan_uniform_fwd_save(const qd_plan* plan, qd_stream_t stream);
 /* gout_i = bwd(src_i, grad_i) for every tensor, in place in grad. */
 int qd_plan_uniform_bwd(const qd_plan* plan, float* const* grad, int mode, qd_stream_t stream);
 
+/* ---- the same for the differentiable-quantization loop (cnn_models/conv_forward_model.py:501-551):
+ * one launch re-quantizes every tensor with its own current list of points (midpoint rule of the
+ * pre-processed path, quant_functions.py:531-573), two small launches produce every tensor's centroid
+ * gradient (:471-506), deterministically.  Per tensor i: src[i] the fixed full-precision tensor,
+ * dst[i] the live parameter (receives q), idx[i] uint8[n], alpha[i] / beta[i] float[rows] (written by
+ * the forward, read by the backward), points[i] float[num_points[i]] ascending, device memory, re-read
+ * at every launch, grad_points[i] float[num_points[i]].  1 <= num_points <= 32 and rows of at most
+ * 1024 elements, otherwise QD_ERR_UNSUPPORTED (use the per-tensor entry points). */
+typedef struct qd_nu_plan qd_nu_plan;
+int qd_plan_nonuniform_create(qd_nu_plan** plan, int count, const float* const* src, float* const* dst,
+                              uint8_t* const* idx, float* const* alpha, float* const* beta,
+                              const float* const* points, float* const* grad_points, const int64_t* n,
+                              const int32_t* num_points, int64_t bucket);
+int qd_plan_nonuniform_destroy(qd_nu_plan* plan);
+int qd_plan_nonuniform_fwd(const qd_nu_plan* plan, qd_stream_t stream);
+/* grad[i]: dLoss/d(quantized tensor i), float[n[i]] */
+int qd_plan_nonuniform_bwd(const qd_nu_plan* plan, const float* const* grad, qd_stream_t stream);
+
 /* ---- host-buffer entry points (what a CPU-tensor caller gets) ------------
  * Inputs and outputs in HOST memory (pinned for full PCIe rate); the call
  * pipelines H2D, the fused kernel and D2H in row-aligned chunks on internal

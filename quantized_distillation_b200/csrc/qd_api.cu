@@ -34,6 +34,14 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+// same, for the other translation units of the library (qd_host.cu)
+extern "C" int qd_internal_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 #define QD_CUDA(call)                                                                         \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
@@ -782,6 +790,131 @@ extern "C" int qd_plan_uniform_bwd(const qd_plan* p, float* const* grad, int mod
     if (mode == QD_BWD_TRUNCATED) return plan_launch<BWD_TRUNC>(p, p->dev_grads, s);
     if (mode == QD_BWD_MINMAX) return plan_launch<BWD_MINMAX>(p, p->dev_grads, s);
     return fail(QD_ERR_INVALID_ARG, "unknown backward mode %d", mode);
+}
+
+// ------------------------------------------------------------------ plan of the differentiable-quantization loop
+struct qd_nu_plan {
+    int count = 0;
+    int64_t bucket = 0;
+    int64_t total_rows = 0, max_row_len = 0, total_blocks = 0;
+    int block_tiles = 1;
+    std::vector<NuEntry> host;
+    NuEntry* dev = nullptr;
+    double* partial = nullptr;
+    float** dev_grads = nullptr;
+};
+
+extern "C" int qd_plan_nonuniform_destroy(qd_nu_plan* p) {
+    if (p == nullptr) return QD_OK;
+    if (p->dev) cudaFree(p->dev);
+    if (p->partial) cudaFree(p->partial);
+    if (p->dev_grads) cudaFree(p->dev_grads);
+    delete p;
+    return QD_OK;
+}
+
+extern "C" int qd_plan_nonuniform_create(qd_nu_plan** out, int count, const float* const* src, float* const* dst,
+                                         uint8_t* const* idx, float* const* alpha, float* const* beta,
+                                         const float* const* points, float* const* grad_points, const int64_t* n,
+                                         const int32_t* num_points, int64_t bucket) {
+    if (out == nullptr || count <= 0 || !src || !dst || !idx || !alpha || !beta || !points || !grad_points || !n || !num_points)
+        return fail(QD_ERR_INVALID_ARG, "bad plan arguments");
+    qd_nu_plan* p = new qd_nu_plan();
+    p->count = count;
+    p->bucket = bucket;
+    p->host.resize(count);
+    int64_t row = 0, tiles = 0;
+    for (int i = 0; i < count; ++i) {
+        Geometry g;
+        if (geometry_of(n[i], bucket, &g) || !src[i] || !dst[i] || !idx[i] || !alpha[i] || !beta[i] || !points[i] || !grad_points[i]) {
+            delete p;
+            return fail(QD_ERR_INVALID_ARG, "bad tensor %d in plan (n=%lld)", i, (long long)n[i]);
+        }
+        if (num_points[i] < 1 || num_points[i] > kNuMaxK || g.row_len > 1024) {
+            delete p;
+            return fail(QD_ERR_UNSUPPORTED, "plan of the centroid op needs 1..%d points and rows of at most 1024 elements "
+                                            "(tensor %d: %d points, rows of %lld)", kNuMaxK, i, num_points[i], (long long)g.row_len);
+        }
+        NuEntry& e = p->host[i];
+        e.src = src[i]; e.dst = dst[i]; e.idx = idx[i]; e.alpha = alpha[i]; e.beta = beta[i]; e.points = points[i];
+        e.grad_points = grad_points[i]; e.n = n[i]; e.row_start = row; e.rows = g.rows; e.row_len = g.row_len; e.K = num_points[i];
+        e.vec = (aligned16(src[i]) && aligned16(dst[i]) && ((reinterpret_cast<uintptr_t>(idx[i]) & 3) == 0) &&
+                 (g.rows == 1 || g.row_len % 4 == 0)) ? 1 : 0;
+        row += g.rows;
+        tiles += (n[i] + kPgTile - 1) / kPgTile;
+        if (g.row_len > p->max_row_len) p->max_row_len = g.row_len;
+    }
+    p->total_rows = row;
+    // gradient blocks: enough of them to fill the machine, fixed for the life of the plan (determinism)
+    int64_t bt = (tiles + 4735) / 4736;
+    p->block_tiles = (int)(bt < 1 ? 1 : (bt > 16 ? 16 : bt));
+    int64_t blk = 0;
+    for (int i = 0; i < count; ++i) {
+        NuEntry& e = p->host[i];
+        const int64_t t = (e.n + kPgTile - 1) / kPgTile;
+        e.blk_start = blk;
+        e.blocks = (t + p->block_tiles - 1) / p->block_tiles;
+        blk += e.blocks;
+    }
+    p->total_blocks = blk;
+    cudaError_t e = cudaMalloc(&p->dev, sizeof(NuEntry) * count);
+    if (e == cudaSuccess) e = cudaMalloc(&p->partial, sizeof(double) * kNuMaxK * (size_t)blk);
+    if (e == cudaSuccess) e = cudaMalloc(&p->dev_grads, sizeof(float*) * count);
+    if (e == cudaSuccess) e = cudaMemcpy(p->dev, p->host.data(), sizeof(NuEntry) * count, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        qd_plan_nonuniform_destroy(p);
+        return fail(QD_ERR_CUDA, "plan allocation: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return QD_OK;
+}
+
+extern "C" int qd_plan_nonuniform_fwd(const qd_nu_plan* p, qd_stream_t stream) {
+    if (p == nullptr) return fail(QD_ERR_INVALID_ARG, "plan is NULL");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t need = (p->total_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+#define QD_NU_LAUNCH(RR)                                                                  \
+    {                                                                                     \
+        auto kern = plan_nonuniform_fwd_kernel<RR>;                                       \
+        const int64_t cap = (int64_t)di->sms * resident_ctas(kern, kWarpCtaThreads, 0);   \
+        const int grid = (int)(need < cap ? need : cap);                                  \
+        kern<<<grid, kWarpCtaThreads, 0, s>>>(p->dev, p->count, p->total_rows);           \
+    }
+    if (p->max_row_len <= 256) QD_NU_LAUNCH(2)
+    else if (p->max_row_len <= 512) QD_NU_LAUNCH(4)
+    else QD_NU_LAUNCH(8)
+#undef QD_NU_LAUNCH
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_plan_nonuniform_bwd(const qd_nu_plan* p, const float* const* grad, qd_stream_t stream) {
+    if (p == nullptr || grad == nullptr) return fail(QD_ERR_INVALID_ARG, "plan or grad is NULL");
+    for (int i = 0; i < p->count; ++i)
+        if (grad[i] == nullptr) return fail(QD_ERR_INVALID_ARG, "grad[%d] is NULL", i);
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t need = (p->total_blocks + kPgWarps - 1) / kPgWarps;
+    const int64_t cap = (int64_t)di->sms * 4;
+    const int grid = (int)(need < cap ? need : cap);
+    if (p->count <= kPlanGradsByValue) {  // pointers ride in the launch parameters (graph-capturable)
+        GradTable gt = {};
+        for (int i = 0; i < p->count; ++i) gt.g[i] = const_cast<float*>(grad[i]);
+        plan_points_grad_partial<0><<<grid, kPgThreads, 0, s>>>(p->dev, p->count, p->total_blocks, p->block_tiles, gt, nullptr, p->partial);
+    } else {
+        static const GradTable kEmpty = {};
+        QD_CUDA(cudaMemcpyAsync(p->dev_grads, grad, sizeof(float*) * p->count, cudaMemcpyHostToDevice, s));
+        plan_points_grad_partial<0><<<grid, kPgThreads, 0, s>>>(p->dev, p->count, p->total_blocks, p->block_tiles, kEmpty, p->dev_grads, p->partial);
+    }
+    QD_CUDA(cudaGetLastError());
+    plan_points_grad_final<<<(p->count + 7) / 8, 256, 0, s>>>(p->dev, p->count, p->partial);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
 }
 
 // ------------------------------------------------------------------ self test

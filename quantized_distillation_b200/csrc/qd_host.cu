@@ -13,16 +13,22 @@
 
 #include "qd_b200.h"
 
+// message of the calling thread (qd_last_error), defined in qd_api.cu
+extern "C" int qd_internal_fail(int code, const char* fmt, ...);
+
+#define QDH_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return qd_internal_fail(QD_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
 namespace {
 
+// pipeline depth and chunk size: three slots of 16 MiB per buffer sit on the plateau of the tuning
+// sweep of round 1 (tools/e2e_tune.py: ~44 GB/s per PCIe direction from 2 slots x 4 MiB upwards)
 constexpr int kMaxSlots = 8;
-// chunk size / pipeline depth, overridable for tuning (QD_HOST_CHUNK_ELEMS, QD_HOST_SLOTS)
-static int64_t env_i64(const char* name, int64_t dflt) {
-    const char* v = getenv(name);
-    return v ? atoll(v) : dflt;
-}
-static const int kSlots = (int)std::min<int64_t>(kMaxSlots, std::max<int64_t>(1, env_i64("QD_HOST_SLOTS", 3)));
-static const int64_t kChunkElems = std::max<int64_t>(1 << 16, env_i64("QD_HOST_CHUNK_ELEMS", 4 << 20));  // 16 MiB per buffer
+constexpr int kSlots = 3;
+constexpr int64_t kChunkElems = 4 << 20;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -41,22 +47,27 @@ struct HostCtx {
 };
 
 HostCtx g_ctx[64];
-std::mutex g_mu;
+std::mutex g_mu[64];  // one lock per device: callers on different GPUs never wait for each other
+
+// the caller's current device is put back when the call returns, whatever the path
+struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int ensure_ctx(int device, HostCtx** out) {
-    if (device < 0 || device >= 64) return QD_ERR_INVALID_ARG;
-    if (cudaSetDevice(device) != cudaSuccess) return QD_ERR_CUDA;
     HostCtx& c = g_ctx[device];
     if (!c.ready) {
         for (int i = 0; i < kSlots; ++i) {
             Slot& s = c.slot[i];
-            if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return QD_ERR_CUDA;
+            QDH_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             const size_t bytes = (size_t)kChunkElems * sizeof(float);
-            if (cudaMalloc(&s.x, bytes) != cudaSuccess || cudaMalloc(&s.g, bytes) != cudaSuccess ||
-                cudaMalloc(&s.q, bytes) != cudaSuccess || cudaMalloc(&s.gout, bytes) != cudaSuccess)
-                return QD_ERR_CUDA;
+            QDH_CUDA(cudaMalloc(&s.x, bytes));
+            QDH_CUDA(cudaMalloc(&s.g, bytes));
+            QDH_CUDA(cudaMalloc(&s.q, bytes));
+            QDH_CUDA(cudaMalloc(&s.gout, bytes));
             s.ws_bytes = qd_workspace_bytes(kChunkElems, 0);
-            if (cudaMalloc(&s.ws, s.ws_bytes) != cudaSuccess) return QD_ERR_CUDA;
+            QDH_CUDA(cudaMalloc(&s.ws, s.ws_bytes));
         }
         c.ready = true;
     }
@@ -66,10 +77,15 @@ int ensure_ctx(int device, HostCtx** out) {
 
 int run_host(const float* hx, const float* hg, float* hq, float* hgout, int64_t n, int64_t bucket, int levels, int mode,
              int device) {
-    if (hx == nullptr || hq == nullptr || n <= 0 || bucket < 0) return QD_ERR_INVALID_ARG;
+    if (hx == nullptr || hq == nullptr || n <= 0 || bucket < 0)
+        return qd_internal_fail(QD_ERR_INVALID_ARG, "host entry point: NULL buffer, n <= 0 or bucket < 0 (n=%lld bucket=%lld)", (long long)n, (long long)bucket);
     const bool bwd = hg != nullptr;
-    if (bwd && hgout == nullptr) return QD_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lk(g_mu);
+    if (bwd && hgout == nullptr) return qd_internal_fail(QD_ERR_INVALID_ARG, "gout_host is NULL");
+    if (device < 0 || device >= 64) return qd_internal_fail(QD_ERR_INVALID_ARG, "device ordinal %d out of range", device);
+    DeviceGuard guard;
+    QDH_CUDA(cudaGetDevice(&guard.prev));
+    QDH_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_mu[device]);
     HostCtx* c;
     int rc = ensure_ctx(device, &c);
     if (rc) return rc;
@@ -85,26 +101,29 @@ int run_host(const float* hx, const float* hg, float* hq, float* hgout, int64_t 
             cudaFree(c->big_x); cudaFree(c->big_g); cudaFree(c->big_q); cudaFree(c->big_gout); cudaFree(c->big_ws);
             const size_t bytes = (size_t)n * sizeof(float);
             c->big_ws_bytes = qd_workspace_bytes(n, bucket);
-            if (cudaMalloc(&c->big_x, bytes) != cudaSuccess || cudaMalloc(&c->big_g, bytes) != cudaSuccess ||
-                cudaMalloc(&c->big_q, bytes) != cudaSuccess || cudaMalloc(&c->big_gout, bytes) != cudaSuccess ||
-                cudaMalloc(&c->big_ws, c->big_ws_bytes) != cudaSuccess) {
-                c->big_cap = 0;
-                return QD_ERR_CUDA;
-            }
+            c->big_cap = 0;
+            c->big_x = c->big_g = c->big_q = c->big_gout = nullptr;
+            c->big_ws = nullptr;
+            QDH_CUDA(cudaMalloc(&c->big_x, bytes));
+            QDH_CUDA(cudaMalloc(&c->big_g, bytes));
+            QDH_CUDA(cudaMalloc(&c->big_q, bytes));
+            QDH_CUDA(cudaMalloc(&c->big_gout, bytes));
+            QDH_CUDA(cudaMalloc(&c->big_ws, c->big_ws_bytes));
             c->big_cap = n;
         }
         cudaStream_t s = c->slot[0].stream;
         const size_t bytes = (size_t)n * sizeof(float);
-        cudaMemcpyAsync(c->big_x, hx, bytes, cudaMemcpyHostToDevice, s);
-        if (bwd) cudaMemcpyAsync(c->big_g, hg, bytes, cudaMemcpyHostToDevice, s);
+        QDH_CUDA(cudaMemcpyAsync(c->big_x, hx, bytes, cudaMemcpyHostToDevice, s));
+        if (bwd) QDH_CUDA(cudaMemcpyAsync(c->big_g, hg, bytes, cudaMemcpyHostToDevice, s));
         rc = bwd ? qd_uniform_fwd_bwd(c->big_x, c->big_g, c->big_q, c->big_gout, n, bucket, levels, mode, c->big_ws,
                                       c->big_ws_bytes, s)
                  : qd_uniform_fwd(c->big_x, c->big_q, nullptr, nullptr, nullptr, nullptr, nullptr, n, bucket, levels,
                                   nullptr, 0.f, 0, 0, 0, c->big_ws, c->big_ws_bytes, s);
         if (rc) return rc;
-        cudaMemcpyAsync(hq, c->big_q, bytes, cudaMemcpyDeviceToHost, s);
-        if (bwd) cudaMemcpyAsync(hgout, c->big_gout, bytes, cudaMemcpyDeviceToHost, s);
-        return cudaStreamSynchronize(s) == cudaSuccess ? QD_OK : QD_ERR_CUDA;
+        QDH_CUDA(cudaMemcpyAsync(hq, c->big_q, bytes, cudaMemcpyDeviceToHost, s));
+        if (bwd) QDH_CUDA(cudaMemcpyAsync(hgout, c->big_gout, bytes, cudaMemcpyDeviceToHost, s));
+        QDH_CUDA(cudaStreamSynchronize(s));
+        return QD_OK;
     }
 
     // row-aligned chunks; the kernel sees each chunk as an independent tensor with the
@@ -120,18 +139,18 @@ int run_host(const float* hx, const float* hg, float* hq, float* hgout, int64_t 
         // a chunk shorter than the bucket must still be bucketed like the tail of the
         // full tensor: with rows >= 2 overall the tail row is "padded", never a short
         // single row -- both cases give the same min/max, so passing bucket is exact.
-        cudaMemcpyAsync(s.x, hx + off, bytes, cudaMemcpyHostToDevice, s.stream);
-        if (bwd) cudaMemcpyAsync(s.g, hg + off, bytes, cudaMemcpyHostToDevice, s.stream);
+        QDH_CUDA(cudaMemcpyAsync(s.x, hx + off, bytes, cudaMemcpyHostToDevice, s.stream));
+        if (bwd) QDH_CUDA(cudaMemcpyAsync(s.g, hg + off, bytes, cudaMemcpyHostToDevice, s.stream));
         rc = bwd ? qd_uniform_fwd_bwd(s.x, s.g, s.q, s.gout, len, bucket, levels, mode, s.ws, s.ws_bytes, s.stream)
                  : qd_uniform_fwd(s.x, s.q, nullptr, nullptr, nullptr, nullptr, nullptr, len, bucket, levels, nullptr,
                                   0.f, 0, 0, 0, s.ws, s.ws_bytes, s.stream);
         if (rc) return rc;
-        cudaMemcpyAsync(hq + off, s.q, bytes, cudaMemcpyDeviceToHost, s.stream);
-        if (bwd) cudaMemcpyAsync(hgout + off, s.gout, bytes, cudaMemcpyDeviceToHost, s.stream);
+        QDH_CUDA(cudaMemcpyAsync(hq + off, s.q, bytes, cudaMemcpyDeviceToHost, s.stream));
+        if (bwd) QDH_CUDA(cudaMemcpyAsync(hgout + off, s.gout, bytes, cudaMemcpyDeviceToHost, s.stream));
     }
-    for (int i = 0; i < kSlots; ++i)
-        if (cudaStreamSynchronize(c->slot[i].stream) != cudaSuccess) return QD_ERR_CUDA;
-    return cudaGetLastError() == cudaSuccess ? QD_OK : QD_ERR_CUDA;
+    for (int i = 0; i < kSlots; ++i) QDH_CUDA(cudaStreamSynchronize(c->slot[i].stream));
+    QDH_CUDA(cudaGetLastError());
+    return QD_OK;
 }
 
 }  // namespace
@@ -142,6 +161,6 @@ extern "C" int qd_uniform_fwd_host(const float* x_host, float* q_host, int64_t n
 
 extern "C" int qd_uniform_fwd_bwd_host(const float* x_host, const float* g_host, float* q_host, float* gout_host,
                                        int64_t n, int64_t bucket, int levels, int mode, int device) {
-    if (g_host == nullptr) return QD_ERR_INVALID_ARG;
+    if (g_host == nullptr) return qd_internal_fail(QD_ERR_INVALID_ARG, "g_host is NULL");
     return run_host(x_host, g_host, q_host, gout_host, n, bucket, levels, mode, device);
 }

@@ -7,6 +7,7 @@
 // over the per-tensor row prefix held in shared memory and then runs exactly
 // the single-tensor warp path on it.
 #pragma once
+#include "qd_points_grad.cuh"
 #include "qd_warp_path.cuh"
 
 namespace qd {
@@ -104,6 +105,215 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_rows_kernel(const PlanEn
         } else {
             warp_process_row<OP_UNIFORM, BWD, R, false, false>(P, cen, rt, row, lane);
         }
+    }
+}
+
+}  // namespace qd
+
+// =============================================================================================
+// Differentiable-quantization loop (cnn_models/conv_forward_model.py:501-551): every step
+// re-quantizes EVERY tensor of the model with its own (changing) list of points and then needs
+// every tensor's centroid gradient.  Per tensor that is 3 launches (forward, gradient partials,
+// gradient fold) x 22-60 tensors; here it is ONE forward launch and TWO small gradient launches
+// for the whole model, all deterministic.
+// =============================================================================================
+namespace qd {
+
+struct NuEntry {
+    const float* src;      // the fixed full-precision tensor (pre-processed path: it never changes)
+    float* dst;            // live parameter, receives the quantized values
+    uint8_t* idx;          // centroid index per element (saved for the backward, :467-468)
+    float* alpha;          // per-row scale (the 'scalingFactor' of the backward) and offset
+    float* beta;
+    const float* points;   // K ascending centroids in [0, 1], device memory, re-read every launch
+    float* grad_points;    // K outputs of the backward
+    int64_t n;
+    int64_t row_start;     // first global row
+    int64_t rows;
+    int64_t row_len;
+    int64_t blk_start;     // first gradient block of this tensor
+    int64_t blocks;        // gradient blocks (each kNuBlockTiles tiles of 1024 elements)
+    int K;                 // 1..32
+    int vec;               // rows 16-byte aligned in src / dst, idx 4-byte aligned
+};
+
+// lane tables of one tensor: thresholds of the midpoint rule straight from the points (:533)
+template <int KP>
+__device__ __forceinline__ void nu_load_tables(LaneSearch<KP>& ls, const float* __restrict__ points, int K, int lane) {
+    const float inf = __int_as_float(0x7f800000);
+    const float k0 = (lane < K) ? __ldg(points + lane) : inf;
+    const float k1 = (lane + 1 < K) ? __ldg(points + lane + 1) : inf;
+    ls.k_lane = k0;
+    ls.t_lane = (lane + 1 < K) ? __fadd_rn(k0, __fmul_rn(__fsub_rn(k1, k0), 0.5f)) : inf;
+    ls.t1 = (KP >= 2) ? __shfl_sync(kFullMask, ls.t_lane, KP / 2 - 1) : 0.f;
+    ls.t2lo = (KP >= 4) ? __shfl_sync(kFullMask, ls.t_lane, KP / 4 - 1) : 0.f;
+    ls.t2hi = (KP >= 4) ? __shfl_sync(kFullMask, ls.t_lane, 3 * KP / 4 - 1) : 0.f;
+}
+
+template <int KP, int R>
+__device__ __forceinline__ void nu_forward_row(const NuEntry& en, int64_t row, int lane) {
+    Params P;
+    P.x = en.src; P.g = nullptr; P.q = en.dst; P.gout = nullptr; P.xhat = nullptr;
+    P.idx8 = en.idx; P.idx64 = nullptr; P.alpha = en.alpha; P.beta = en.beta; P.argmin = nullptr; P.argmax = nullptr;
+    P.mean = nullptr; P.max_element = 0.f; P.points = en.points; P.num_points = en.K; P.rule = QD_RULE_MIDPOINT;
+    P.geo.n = en.n; P.geo.row_len = en.row_len; P.geo.rows = en.rows;
+    P.S = 0.f; P.rS = 0.f; P.half_minus_band = 0.f; P.stochastic = 0; P.seed = 0; P.offset = 0;
+    LaneSearch<KP> ls;
+    nu_load_tables<KP>(ls, en.points, en.K, lane);
+    const Centroids cen{nullptr, nullptr, en.K};
+    const bool full = (en.row_len == R * 128) && ((row + 1) * en.row_len <= en.n);
+    float v[4 * R], gv[4 * R];
+    if (en.vec) {
+        if (full) {
+            warp_load_row<OP_NONUNIFORM, KP, R, true, true>(P, row, lane, v, gv);
+            warp_compute_row<OP_NONUNIFORM, KP, R, true, true>(P, cen, ls, row, lane, v, gv);
+        } else {
+            warp_load_row<OP_NONUNIFORM, KP, R, true, false>(P, row, lane, v, gv);
+            warp_compute_row<OP_NONUNIFORM, KP, R, true, false>(P, cen, ls, row, lane, v, gv);
+        }
+    } else {
+        warp_load_row<OP_NONUNIFORM, KP, R, false, false>(P, row, lane, v, gv);
+        warp_compute_row<OP_NONUNIFORM, KP, R, false, false>(P, cen, ls, row, lane, v, gv);
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kWarpCtaThreads) plan_nonuniform_fwd_kernel(const NuEntry* __restrict__ entries, int count,
+                                                                             int64_t total_rows) {
+    __shared__ int64_t s_start[kPlanSmemEntries];
+    const bool in_smem = count <= kPlanSmemEntries;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) s_start[i] = entries[i].row_start;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t grow = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); grow < total_rows; grow += stride) {
+        int lo = 0, hi = count - 1;  // largest t with row_start[t] <= grow
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            const int64_t s = in_smem ? s_start[mid] : entries[mid].row_start;
+            if (s <= grow) lo = mid; else hi = mid - 1;
+        }
+        const NuEntry en = entries[lo];
+        const int64_t row = grow - en.row_start;
+        // table size class: warp-uniform (one tensor per row)
+        if (en.K <= 4) nu_forward_row<4, R>(en, row, lane);
+        else if (en.K <= 8) nu_forward_row<8, R>(en, row, lane);
+        else if (en.K <= 16) nu_forward_row<16, R>(en, row, lane);
+        else nu_forward_row<32, R>(en, row, lane);
+    }
+}
+
+// ---- centroid gradients of every tensor (quant_functions.py:471-506) -----------------------
+// grad_points[t][k] = sum_{i in tensor t : idx_i = k} fl32(g_i * alpha_row(i)).  A gradient BLOCK is a
+// fixed run of kNuBlockTiles tiles (1024 elements each) inside ONE tensor; one warp reduces one block
+// with the conflict-free per-lane column scheme of qd_points_grad.cuh into K float64 partials, a second
+// launch folds each tensor's blocks in index order.  The block size is fixed when the plan is built,
+// so the summation tree -- and the result -- is the same on every replica and every step.
+constexpr int kNuMaxK = 32;
+
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(kPgThreads) plan_points_grad_partial(const NuEntry* __restrict__ entries, int count,
+                                                                      int64_t total_blocks, int block_tiles,
+                                                                      const __grid_constant__ GradTable gtab,
+                                                                      float* const* __restrict__ grads,
+                                                                      double* __restrict__ partial /*[total_blocks][32]*/) {
+    __shared__ float s_col[kPgWarps][kNuMaxK][32];
+    __shared__ int64_t s_bstart[kPlanSmemEntries];
+    const bool in_smem = count <= kPlanSmemEntries;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) s_bstart[i] = entries[i].blk_start;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float(*col)[32] = s_col[warp];
+    const int64_t stride = (int64_t)gridDim.x * kPgWarps;
+    for (int64_t blk = (int64_t)blockIdx.x * kPgWarps + warp; blk < total_blocks; blk += stride) {
+        int lo = 0, hi = count - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            const int64_t s = in_smem ? s_bstart[mid] : entries[mid].blk_start;
+            if (s <= blk) lo = mid; else hi = mid - 1;
+        }
+        const NuEntry en = entries[lo];
+        const float* g = (grads != nullptr) ? grads[lo] : gtab.g[lo];
+        const uint8_t* idx = en.idx;
+        const int K = en.K;
+        for (int k = 0; k < K; ++k) col[k][lane] = 0.f;
+        __syncwarp();
+        double acc = 0.0;  // lane k < K owns centroid k's float64 sum
+        const int64_t tile0 = (blk - en.blk_start) * block_tiles;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 3) == 0);
+        int since_flush = 0;
+        for (int tt = 0; tt < block_tiles; ++tt) {
+            const int64_t start = (tile0 + tt) * kPgTile;
+            if (start >= en.n) break;
+            const int len = (int)min((int64_t)kPgTile, en.n - start);
+            if (vec_ok && len == kPgTile && (en.rows == 1 || en.row_len % 128 == 0)) {
+                float4 gv[8];
+                uint32_t iw[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    gv[j] = ld_stream4(g + start + j * 128 + lane * 4);
+                    iw[j] = *reinterpret_cast<const uint32_t*>(idx + start + j * 128 + lane * 4);
+                }
+                int64_t row = (en.rows == 1) ? 0 : start / en.row_len;
+                int64_t rem = (en.rows == 1) ? 0 : start - row * en.row_len;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a = en.alpha[row];
+                    if (en.rows != 1) {
+                        rem += 128;
+                        if (rem >= en.row_len) { rem -= en.row_len; ++row; }
+                    }
+                    const float pv[4] = {__fmul_rn(gv[j].x, a), __fmul_rn(gv[j].y, a), __fmul_rn(gv[j].z, a), __fmul_rn(gv[j].w, a)};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const unsigned id = (iw[j] >> (8 * c)) & 0xffu;
+                        if (id < (unsigned)K) col[id][lane] += pv[c];
+                    }
+                }
+            } else {
+                for (int e = lane; e < len; e += 32) {
+                    const int64_t ge = start + e;
+                    const float a = (en.rows == 1) ? en.alpha[0] : en.alpha[ge / en.row_len];
+                    const unsigned id = idx[ge];
+                    if (id < (unsigned)K) col[id][lane] += __fmul_rn(g[ge], a);
+                }
+            }
+            if (++since_flush == kPgFlushEvery) {  // float32 columns only ever add a few hundred terms
+                since_flush = 0;
+                __syncwarp();
+                for (int k = 0; k < K; ++k) {
+                    const double s = warp_sum((double)col[k][lane]);
+                    col[k][lane] = 0.f;
+                    if (lane == k) acc += s;
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < K; ++k) {
+            const double s = warp_sum((double)col[k][lane]);
+            if (lane == k) acc += s;
+        }
+        __syncwarp();
+        if (lane < K) partial[blk * kNuMaxK + lane] = acc;
+    }
+}
+
+// one warp per tensor: lane k folds the tensor's blocks in index order
+__global__ void __launch_bounds__(256) plan_points_grad_final(const NuEntry* __restrict__ entries, int count,
+                                                              const double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= count) return;
+    const NuEntry en = entries[t];
+    if (lane < en.K) {
+        double s = 0.0;
+        for (int64_t b = 0; b < en.blocks; ++b) s += partial[(en.blk_start + b) * kNuMaxK + lane];
+        en.grad_points[lane] = (float)s;
     }
 }
 

@@ -103,3 +103,84 @@ class QuantizationPlan:
             self.close()
         except Exception:
             pass
+
+
+class CentroidPlan:
+    """Multi-tensor plan of the differentiable-quantization loop
+    (cnn_models/conv_forward_model.py:501-551): ``forward_()`` re-quantizes every tensor with its
+    own current points in ONE launch (quantized values straight into the live parameters, uint8
+    indices and per-row scales kept for the backward), ``backward_(grads)`` returns every tensor's
+    centroid gradient from TWO launches -- instead of three launches per tensor per step.
+
+    ``sources`` are the fixed full-precision tensors (the loop never changes them), ``targets`` the
+    live parameters of the quantized copy of the model, ``points`` the per-tensor 1-D point
+    tensors; the optimizer must update those IN PLACE (their addresses are in the plan).
+    Raises ``NotImplementedError`` for more than 32 points or rows longer than 1024 elements:
+    callers fall back to the per-tensor ops."""
+
+    MAX_POINTS = 32
+
+    def __init__(self, sources, targets, points, bucket_size=None):
+        N.require_cuda()
+        count = len(sources)
+        if count == 0 or len(targets) != count or len(points) != count:
+            raise ValueError("one source, target and point tensor per quantized tensor expected")
+        for t in list(sources) + list(targets) + list(points):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("plan tensors must be contiguous float32 CUDA tensors")
+        self.device = sources[0].device
+        self.sources, self.targets, self.points = list(sources), list(targets), list(points)
+        self.bucket_size = bucket_size
+        b = 0 if bucket_size is None else int(bucket_size)
+        geo = [N.geometry(s.numel(), b) for s in sources]
+        pad = lambda n, g: -(-n // g) * g
+        self._idx_flat = torch.empty(sum(pad(s.numel(), 256) for s in sources), dtype=torch.uint8, device=self.device)
+        self._scale_flat = torch.empty(2 * sum(pad(rows, 64) for rows, _, _ in geo), dtype=torch.float32, device=self.device)
+        self._gp_flat = torch.zeros(count * self.MAX_POINTS, dtype=torch.float32, device=self.device)
+        self.indices, self.alpha, self.beta, self.grad_points = [], [], [], []
+        io = so = 0
+        for i, (s, (rows, _, _)) in enumerate(zip(sources, geo)):
+            self.indices.append(self._idx_flat[io:io + s.numel()].view(s.shape))
+            io += pad(s.numel(), 256)
+            self.alpha.append(self._scale_flat[so:so + rows])
+            so += pad(rows, 64)
+            self.beta.append(self._scale_flat[so:so + rows])
+            so += pad(rows, 64)
+            self.grad_points.append(self._gp_flat[i * self.MAX_POINTS:i * self.MAX_POINTS + points[i].numel()])
+        arr = lambda ts: (C.c_void_p * count)(*[t.data_ptr() for t in ts])
+        self._n = (C.c_int64 * count)(*[s.numel() for s in sources])
+        self._k = (C.c_int32 * count)(*[p.numel() for p in points])
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().qd_plan_nonuniform_create(C.byref(self._handle), count, arr(sources), arr(targets), arr(self.indices),
+                                                      arr(self.alpha), arr(self.beta), arr(points), arr(self.grad_points),
+                                                      self._n, self._k, b))
+
+    def forward_(self):
+        """targets <- nonUniformQuantization(sources, points) for every tensor, one launch (:525-532)."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib().qd_plan_nonuniform_fwd(self._handle, N.stream_ptr(self.device)))
+
+    def backward_(self, grads):
+        """Every tensor's dLoss/dpoints from dLoss/d(quantized tensor) (:539-545); returns views of one
+        flat buffer, overwritten by the next call."""
+        if len(grads) != len(self.sources):
+            raise ValueError("one gradient per tensor expected")
+        for g, s in zip(grads, self.sources):
+            if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == s.numel()):
+                raise ValueError("gradients must be contiguous float32 CUDA tensors matching the tensors")
+        gp = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(self.device):
+            N.check(N.lib().qd_plan_nonuniform_bwd(self._handle, gp, N.stream_ptr(self.device)))
+        return self.grad_points
+
+    def close(self):
+        if self._handle:
+            N.lib().qd_plan_nonuniform_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

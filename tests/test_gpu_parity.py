@@ -564,6 +564,57 @@ def test_multi_tensor_plan_matches_per_tensor(Q):
                 assert torch.equal(g, e)
 
 
+def test_centroid_plan_matches_per_tensor_ops_and_oracle(Q):
+    """qd_plan_nonuniform_fwd / _bwd: every tensor of a model in one forward launch and two gradient
+    launches.  q and idx bit-identical to the per-tensor op and to the oracle (midpoint rule), centroid
+    gradients equal to the oracle's float64 sums within float32 rounding, deterministic across calls."""
+    from quantized_distillation_b200.plan import CentroidPlan
+    rng = np.random.default_rng(41)
+    sizes = [5000, 10, 5625, 75, 93750, 50, 800000, 500, 25, 1, 257, 255]          # student-like mix incl. tiny tensors
+    for bucket in (256, 1024, 100, None):
+        if bucket is None:
+            use = [n for n in sizes if n <= 1024]
+        else:
+            use = sizes
+        Ks = [int(rng.integers(1, 33)) for _ in use]
+        Ks[0], Ks[1] = 4, 32
+        xs = [(rng.standard_normal(n) * 0.05).astype(np.float32) for n in use]
+        pts = [np.sort(rng.random(k)).astype(np.float32) for k in Ks]
+        gs = [rng.standard_normal(n).astype(np.float32) for n in use]
+        src = [dev(x) for x in xs]
+        dst = [torch.empty_like(t) for t in src]
+        pd = [dev(p) for p in pts]
+        plan = CentroidPlan(src, dst, pd, bucket)
+        plan.forward_()
+        grads = plan.backward_([dev(g) for g in gs])
+        first = [g.clone() for g in grads]
+        for i, (x, p, g) in enumerate(zip(xs, pts, gs)):
+            q, idx, st = O.nonuniform_fwd(x, p, bucket, rule="midpoint")
+            assert_same(dst[i].cpu().numpy(), q, f"plan q tensor {i} b={bucket}")
+            assert_same(plan.indices[i].cpu().numpy().astype(np.int64).reshape(-1), idx.reshape(-1), f"plan idx tensor {i}")
+            assert_same(plan.alpha[i].cpu().numpy(), st["alpha"], "plan alpha")
+            f = Q.nonUniformQuantization_variable(bucket_size=bucket, pre_process_tensors=True, tensor=src[i])
+            assert torch.equal(f.forward(None, pd[i]).view(-1), dst[i].view(-1))
+            ref = O.nonuniform_bwd_points(g, idx, st["alpha"], len(p), bucket)
+            got = first[i].cpu().numpy().astype(np.float64)
+            mag = np.array([np.abs(g.reshape(-1)[idx.reshape(-1) == k]).sum() for k in range(len(p))]) * float(st["alpha"].max())
+            assert np.all(np.abs(got - ref) <= 1e-6 * mag + 2.0 ** -23 * np.abs(ref) + 1e-30), (i, bucket, got, ref)
+        # new points, same plan: the table is re-read at every launch; gradients reproducible bit for bit
+        for p in pd:
+            p.copy_(torch.sort(torch.rand_like(p))[0])
+        plan.forward_()
+        for i, x in enumerate(xs):
+            q, idx, _ = O.nonuniform_fwd(x, pd[i].cpu().numpy(), bucket, rule="midpoint")
+            assert_same(dst[i].cpu().numpy(), q, f"plan q after point update, tensor {i}")
+        a = [g.clone() for g in plan.backward_([dev(g) for g in gs])]
+        b = [g.clone() for g in plan.backward_([dev(g) for g in gs])]
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+    with pytest.raises(NotImplementedError):
+        CentroidPlan([dev(xs[0])], [torch.empty(len(xs[0]), device="cuda")], [torch.linspace(0, 1, 33, device="cuda")], 256)
+    with pytest.raises(NotImplementedError):
+        CentroidPlan([dev(xs[0])], [torch.empty(len(xs[0]), device="cuda")], [torch.linspace(0, 1, 4, device="cuda")], 2048)
+
+
 def test_error_mapping(Q):
     x = torch.randn(100).cuda()
     with pytest.raises(ValueError):

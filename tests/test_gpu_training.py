@@ -233,3 +233,27 @@ def test_mix_with_differentiable_quantization_two_epochs(env, graph):
     for p in params:                                                   # returned weights are 2-bit quantized per bucket
         assert distinct_per_bucket(p, 256) <= 4
         assert torch.isfinite(p).all()
+
+
+def test_diffquant_multi_tensor_plan_matches_per_tensor_loop(env):
+    """optimize_quantization_points with the CentroidPlan (3 launches per step for the whole model)
+    against the same loop on the per-tensor ops (3 launches per tensor): same quantized weights bit
+    for bit at every step, points equal up to the summation order of the centroid gradients."""
+    Q, cfm, hf = env
+    torch.backends.cudnn.deterministic = True
+    outs = []
+    for use_plan in (True, False):
+        torch.manual_seed(3)
+        model = make_student(cfm)
+        data = hf.synthetic_cifar_loader(5, 25, seed=6)
+        state, points, info = cfm.optimize_quantization_points(
+            model, data, data, initial_learning_rate=1e-4, epochs_to_train=1, print_every=5, numPointsPerTensor=4,
+            bucket_size=256, use_distillation_loss=True, initialize_method="quantiles", verbose=False, evaluate=False,
+            use_cuda_graphs=False, use_plan=use_plan)
+        assert info["multi_tensor_plan"] is use_plan and info["numStepsTrained"] == 5
+        outs.append(([p.detach().clone() for p in points], state))
+    torch.backends.cudnn.deterministic = False
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (a, b)
+    agree = [float((outs[0][1][k] == outs[1][1][k]).float().mean()) for k in outs[0][1] if outs[0][1][k].dtype == torch.float32]
+    assert min(agree) > 0.999, min(agree)                     # a point moving by an ulp can flip a boundary element
