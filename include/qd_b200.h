@@ -164,6 +164,17 @@ int qd_plan_uniform_fwd_save(const qd_plan* plan, qd_stream_t stream);
 /* gout_i = bwd(src_i, grad_i) for every tensor, in place in grad. */
 int qd_plan_uniform_bwd(const qd_plan* plan, float* const* grad, int mode, qd_stream_t stream);
 
+/* Fused end-of-step: for every tensor, in ONE pass (24 bytes per element):
+ *   grad    <- fix-up of `mode` evaluated at the full-precision shadow copy   (conv_forward_model.py:249-266, :315)
+ *   shadow, momentum <- torch.optim.SGD update (momentum, Nesterov, weight decay, dampening 0)   (:317)
+ *   dst     <- uniformQuantization(shadow)   -- the next step's quantized weights            (:286-287)
+ * QD_BWD_TRUNCATED also clamps the updated weights to [-1, 1] (the next step's clamp, :240-241).
+ * momentum[i]: n[i] floats, zero before the first step.  Rows of at most 512 elements, else QD_ERR_UNSUPPORTED.
+ * Arithmetic = torch's CUDA SGD kernels (a + alpha*b contracted to one FMA): see qd_plan.cuh. */
+int qd_plan_set_momentum(qd_plan* plan, float* const* momentum);
+int qd_plan_sgd_step(const qd_plan* plan, float* const* grad, int mode, double lr, double momentum,
+                     double weight_decay, int nesterov, qd_stream_t stream);
+
 /* ---- the same for the differentiable-quantization loop (cnn_models/conv_forward_model.py:501-551):
  * one launch re-quantizes every tensor with its own current list of points (midpoint rule of the
  * pre-processed path, quant_functions.py:531-573), two small launches produce every tensor's centroid

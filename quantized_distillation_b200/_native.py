@@ -46,6 +46,8 @@ SIGNATURES = {
     "qd_plan_uniform_fwd": (C.c_int, [_p, _p]),
     "qd_plan_uniform_fwd_save": (C.c_int, [_p, _p]),
     "qd_plan_uniform_bwd": (C.c_int, [_p, _p, _i32, _p]),
+    "qd_plan_set_momentum": (C.c_int, [_p, _p]),
+    "qd_plan_sgd_step": (C.c_int, [_p, _p, _i32, C.c_double, C.c_double, C.c_double, _i32, _p]),
     "qd_plan_nonuniform_create": (C.c_int, [C.POINTER(_p), _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64]),
     "qd_plan_nonuniform_destroy": (C.c_int, [_p]),
     "qd_plan_nonuniform_fwd": (C.c_int, [_p, _p]),

@@ -643,6 +643,7 @@ struct qd_plan {
     int64_t max_row_len = 0;
     bool warp_path = true;
     bool has_shadow = false;
+    bool has_momentum = false;
     std::vector<PlanEntry> host;
     PlanEntry* dev = nullptr;
     float** dev_grads = nullptr;  // count pointers, refreshed per backward call
@@ -669,7 +670,7 @@ extern "C" int qd_plan_create(qd_plan** out, int count, const float* const* src,
             return fail(QD_ERR_INVALID_ARG, "bad tensor %d in plan (n=%lld levels=%d)", i, (long long)n[i], levels[i]);
         }
         PlanEntry& e = p->host[i];
-        e.src = src[i]; e.dst = dst[i]; e.save = nullptr; e.n = n[i]; e.row_start = row; e.rows = g.rows; e.row_len = g.row_len;
+        e.src = src[i]; e.dst = dst[i]; e.save = nullptr; e.mom = nullptr; e.n = n[i]; e.row_start = row; e.rows = g.rows; e.row_len = g.row_len;
         e.S = (float)(levels[i] - 1);
         e.rS = 1.0f / e.S;
         e.lim = 0.5f - e.S * 0x1p-20f;
@@ -711,6 +712,68 @@ extern "C" int qd_plan_set_shadow(qd_plan* p, float* const* shadow) {
     QD_CUDA(cudaMemcpy(p->dev, p->host.data(), sizeof(PlanEntry) * p->count, cudaMemcpyHostToDevice));
     p->has_shadow = true;
     return QD_OK;
+}
+
+extern "C" int qd_plan_set_momentum(qd_plan* p, float* const* momentum) {
+    if (p == nullptr || momentum == nullptr) return fail(QD_ERR_INVALID_ARG, "plan or momentum is NULL");
+    for (int i = 0; i < p->count; ++i) {
+        if (momentum[i] == nullptr) return fail(QD_ERR_INVALID_ARG, "momentum[%d] is NULL", i);
+        p->host[i].mom = momentum[i];
+    }
+    QD_CUDA(cudaMemcpy(p->dev, p->host.data(), sizeof(PlanEntry) * p->count, cudaMemcpyHostToDevice));
+    p->has_momentum = true;
+    return QD_OK;
+}
+
+template <int BWD>
+static int plan_sgd_launch(const qd_plan* p, float* const* dev_grads, const GradTable& gt, const SgdParams& sp, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    const int64_t need = (p->total_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+#define QD_SGD_LAUNCH(RR)                                                                          \
+    {                                                                                              \
+        auto kern = plan_sgd_step_kernel<BWD, RR>;                                                 \
+        const int64_t cap = (int64_t)di->sms * resident_ctas(kern, kWarpCtaThreads, 0);            \
+        const int grid = (int)(need < cap ? need : cap);                                           \
+        kern<<<grid, kWarpCtaThreads, 0, s>>>(p->dev, p->count, p->total_rows, dev_grads, gt, sp); \
+    }
+    if (p->max_row_len <= 256) QD_SGD_LAUNCH(2)
+    else QD_SGD_LAUNCH(4)
+#undef QD_SGD_LAUNCH
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_plan_sgd_step(const qd_plan* p, float* const* grad, int mode, double lr, double momentum,
+                                double weight_decay, int nesterov, qd_stream_t stream) {
+    if (p == nullptr || grad == nullptr) return fail(QD_ERR_INVALID_ARG, "plan or grad is NULL");
+    if (!p->has_shadow || !p->has_momentum) return fail(QD_ERR_INVALID_ARG, "qd_plan_set_shadow and qd_plan_set_momentum must be called first");
+    if (p->max_row_len > 512) return fail(QD_ERR_UNSUPPORTED, "fused optimizer step needs rows of at most 512 elements (plan has %lld)", (long long)p->max_row_len);
+    if (mode == QD_BWD_MINMAX && p->bucket == 0)
+        return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
+    if (nesterov && !(momentum > 0.0)) return fail(QD_ERR_INVALID_ARG, "Nesterov momentum requires a momentum");   // torch.optim.SGD's own check
+    for (int i = 0; i < p->count; ++i)
+        if (grad[i] == nullptr) return fail(QD_ERR_INVALID_ARG, "grad[%d] is NULL", i);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    SgdParams sp;
+    sp.lr = (float)lr; sp.momentum = (float)momentum; sp.weight_decay = (float)weight_decay; sp.nesterov = nesterov ? 1 : 0;
+    static const GradTable kEmpty = {};
+    GradTable gt = {};
+    float* const* dev_grads = nullptr;
+    if (p->count <= kPlanGradsByValue) {
+        for (int i = 0; i < p->count; ++i) gt.g[i] = grad[i];
+    } else {
+        QD_CUDA(cudaMemcpyAsync(p->dev_grads, grad, sizeof(float*) * p->count, cudaMemcpyHostToDevice, s));
+        dev_grads = p->dev_grads;
+    }
+    const GradTable& g = dev_grads ? kEmpty : gt;
+    switch (mode) {
+        case QD_BWD_STE: return plan_sgd_launch<BWD_STE>(p, dev_grads, g, sp, s);
+        case QD_BWD_TRUNCATED: return plan_sgd_launch<BWD_TRUNC>(p, dev_grads, g, sp, s);
+        case QD_BWD_MINMAX: return plan_sgd_launch<BWD_MINMAX>(p, dev_grads, g, sp, s);
+        default: return fail(QD_ERR_INVALID_ARG, "unknown backward mode %d", mode);
+    }
 }
 
 template <int BWD>

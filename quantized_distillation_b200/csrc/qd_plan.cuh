@@ -16,6 +16,7 @@ struct PlanEntry {
     const float* src;
     float* dst;
     float* save;        // optional: full-precision copy of src written by the forward launch (shadow buffer)
+    float* mom;         // optional: momentum buffer of the fused optimizer step
     int64_t n;
     int64_t row_start;  // first global row of this tensor
     int64_t rows;
@@ -314,6 +315,189 @@ __global__ void __launch_bounds__(256) plan_points_grad_final(const NuEntry* __r
         double s = 0.0;
         for (int64_t b = 0; b < en.blocks; ++b) s += partial[(en.blk_start + b) * kNuMaxK + lane];
         en.grad_points[lane] = (float)s;
+    }
+}
+
+}  // namespace qd
+
+// =============================================================================================
+// f1, second half: the end of one quantized-distillation step and the beginning of the next in ONE
+// pass over the model (cnn_models/conv_forward_model.py:302-317 then :286-287 of the next step):
+//
+//     g      <- gradient fix-up of the chosen style, evaluated at the full-precision master w
+//     m, w   <- SGD with momentum / Nesterov / weight decay (torch.optim.SGD arithmetic, see below)
+//     master <- w                     (what load_state_dict / state_dict kept alive)
+//     live   <- uniformQuantization(w)   (what the next forward pass sees)
+//
+// 24 bytes per element (read w, g, m; write w, m, q) instead of restore 8 + fix-up 12 + SGD 20 +
+// save-and-quantize 12.  FMA policy = what torch's multi-tensor SGD kernels compute on CUDA, where
+// `a + alpha * b` is contracted:  gd = fma(wd, w, g);  m' = RN(RN(mu*m) + gd)  (mul_ then add_ are two
+// kernels there);  gn = fma(mu, m', gd) (Nesterov) or m';  w' = fma(-lr, gn, w).  The first step
+// starts from m = 0, which gives m' = gd like torch's clone of the gradient.
+// =============================================================================================
+namespace qd {
+
+struct SgdParams {
+    float lr, momentum, weight_decay;
+    int nesterov;
+};
+
+// q of a whole row held in registers (every lane, every slot; slots past the row end hold zeros)
+template <int E>
+__device__ __forceinline__ void quantize_row_regs(const float (&v)[E], float alpha, float beta, float S, float rS, float lim,
+                                                  float (&qv)[E]) {
+    const UniformFast uf = make_uniform_fast(alpha, S);
+    if (uf.ok) {
+        float lv[E];
+        bool unsafe = false;
+#pragma unroll
+        for (int i = 0; i < E; ++i) lv[i] = fast_level(v[i], beta, uf.c, lim, unsafe);
+        if (__any_sync(kFullMask, unsafe)) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) lv[i] = exact_level(v[i], beta, alpha, S);
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) qv[i] = from_unit(small_level_to_unit(lv[i], S, rS), alpha, beta);
+    } else {
+#pragma unroll
+        for (int i = 0; i < E; ++i) qv[i] = exact_quantize(v[i], beta, alpha, S).x;
+    }
+}
+
+template <int R, bool VEC, bool FULL>
+__device__ __forceinline__ void row_min_max(const float (&v)[4 * R], int len, int lane, float& mn, float& mx) {
+    mn = __int_as_float(0x7f800000);
+    mx = __int_as_float(0xff800000);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (FULL || elem_index<R, VEC>(r, j, lane) < len) {
+                mn = min_nan(mn, v[4 * r + j]);
+                mx = max_nan(mx, v[4 * r + j]);
+            }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+}
+
+template <int BWD, int R, bool VEC, bool FULL>
+__device__ __forceinline__ void sgd_step_row(const PlanEntry& en, float* __restrict__ grad, float* __restrict__ mom,
+                                             const SgdParams& sp, int64_t row, int lane) {
+    constexpr int E = 4 * R;
+    const int64_t base = row * en.row_len;
+    const int len = FULL ? R * 128 : (int)min(en.row_len, en.n - base);
+    float w[E], g[E], m[E], q[E];
+    load_row<R, VEC, FULL>(en.save + base, len, lane, w);   // full-precision master
+    load_row<R, VEC, FULL>(grad + base, len, lane, g);
+    load_row<R, VEC, FULL>(mom + base, len, lane, m);
+
+    // ---- gradient fix-up at the master weights (conv_forward_model.py:249-266) ----------------
+    if constexpr (BWD == BWD_TRUNC) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) g[i] = (fabsf(w[i]) > 1.0f) ? 0.f : g[i];
+    } else if constexpr (BWD == BWD_MINMAX) {
+        float mn, mx;
+        row_min_max<R, VEC, FULL>(w, len, lane, mn, mx);
+        RowState rs;
+        rs.mean = 0.f;
+        rs.beta = mn;
+        rs.alpha = make_alpha(mn, mx);
+        quantize_row_regs<E>(w, rs.alpha, rs.beta, en.S, en.rS, en.lim, q);
+        // second scaling of q (quant_functions.py:350-363): same reductions, same order as the plan's
+        // backward launch (warp_compute_row), so fused and unfused steps agree bit for bit
+        float qmn = __int_as_float(0x7f800000), qmx = __int_as_float(0xff800000);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (FULL || elem_index<R, VEC>(r, j, lane) < len) {
+                    qmn = min_nan(qmn, q[4 * r + j]);
+                    qmx = max_nan(qmx, q[4 * r + j]);
+                }
+        qmn = warp_min(qmn);
+        qmx = warp_max(qmx);
+        rs.beta2 = qmn;
+        rs.alpha2 = make_alpha(qmn, qmx);
+        const int imin = first_equal<R, VEC, FULL>(q, qmn, len, lane);
+        const int imax = first_equal<R, VEC, FULL>(q, qmx, len, lane);
+        double acc = 0.0;
+        const RowDivider div2(rs.alpha2);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (FULL || elem_index<R, VEC>(r, j, lane) < len)
+                    acc += (double)minmax_term(w[4 * r + j], q[4 * r + j], g[4 * r + j], rs.beta2, div2);
+        const float rb = (float)warp_sum(acc);
+        if (imin != imax) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = elem_index<R, VEC>(r, j, lane);
+                    if (e == imax) g[4 * r + j] = __fadd_rn(g[4 * r + j], rb);
+                    if (e == imin) g[4 * r + j] = __fadd_rn(g[4 * r + j], -rb);
+                }
+        }
+    }
+
+    // ---- torch.optim.SGD (dampening 0) ----------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        float gd = g[i];
+        if (sp.weight_decay != 0.f) gd = __fmaf_rn(sp.weight_decay, w[i], gd);
+        float step = gd;
+        if (sp.momentum != 0.f) {
+            m[i] = __fadd_rn(__fmul_rn(m[i], sp.momentum), gd);
+            step = sp.nesterov ? __fmaf_rn(sp.momentum, m[i], gd) : m[i];
+        }
+        w[i] = __fmaf_rn(-sp.lr, step, w[i]);
+        if constexpr (BWD == BWD_TRUNC) w[i] = fminf(fmaxf(w[i], -1.0f), 1.0f);   // next step's p.data.clamp_(-1, 1) (:240-241)
+    }
+    store_row<R, VEC, FULL>(en.save + base, len, lane, w);
+    if (sp.momentum != 0.f) store_row<R, VEC, FULL>(mom + base, len, lane, m);
+
+    // ---- next step's quantization of the updated weights -----------------------------------------
+    float mn, mx;
+    row_min_max<R, VEC, FULL>(w, len, lane, mn, mx);
+    const float alpha = make_alpha(mn, mx);
+    quantize_row_regs<E>(w, alpha, mn, en.S, en.rS, en.lim, q);
+    store_row<R, VEC, FULL>(en.dst + base, len, lane, q);
+}
+
+template <int BWD, int R>
+__global__ void __launch_bounds__(kWarpCtaThreads) plan_sgd_step_kernel(const PlanEntry* __restrict__ entries, int count,
+                                                                       int64_t total_rows, float* const* __restrict__ grads,
+                                                                       const __grid_constant__ GradTable gtab,
+                                                                       const SgdParams sp) {
+    __shared__ int64_t s_start[kPlanSmemEntries];
+    const bool in_smem = count <= kPlanSmemEntries;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) s_start[i] = entries[i].row_start;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t grow = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); grow < total_rows; grow += stride) {
+        int lo = 0, hi = count - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            const int64_t s = in_smem ? s_start[mid] : entries[mid].row_start;
+            if (s <= grow) lo = mid; else hi = mid - 1;
+        }
+        const PlanEntry en = entries[lo];
+        float* grad = (grads != nullptr) ? grads[lo] : gtab.g[lo];
+        float* mom = en.mom;
+        const int64_t row = grow - en.row_start;
+        const bool vec = en.vec != 0 && ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(mom) |
+                                          reinterpret_cast<uintptr_t>(en.save)) & 15) == 0;
+        const bool full = (en.row_len == R * 128) && ((row + 1) * en.row_len <= en.n);
+        if (vec) {
+            if (full) sgd_step_row<BWD, R, true, true>(en, grad, mom, sp, row, lane);
+            else sgd_step_row<BWD, R, true, false>(en, grad, mom, sp, row, lane);
+        } else {
+            sgd_step_row<BWD, R, false, false>(en, grad, mom, sp, row, lane);
+        }
     }
 }
 

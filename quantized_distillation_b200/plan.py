@@ -51,6 +51,8 @@ class QuantizationPlan:
             self._master.append(self._master_flat[off:off + p.numel()].view(p.shape))
             off += -(-p.numel() // 64) * 64
         self.numel = total
+        self._momentum_flat = None
+        self.momentum_buffers = None
         self._shadow_ptrs = (C.c_void_p * count)(*[m.data_ptr() for m in self._master])
         with torch.cuda.device(self.device):
             N.check(N.lib().qd_plan_set_shadow(self._handle, self._shadow_ptrs))
@@ -92,6 +94,30 @@ class QuantizationPlan:
         gp = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
         with torch.cuda.device(self.device):
             N.check(N.lib().qd_plan_uniform_bwd(self._handle, gp, mode, N.stream_ptr(self.device)))
+
+    def fused_step_(self, grads, style, lr, momentum=0.0, weight_decay=0.0, nesterov=False):
+        """End of step i and start of step i+1 in ONE pass over the model (24 B/elt): gradient fix-up of
+        ``style`` at the master weights, ``torch.optim.SGD`` update of master + momentum buffer, and the
+        live parameters re-quantized from the updated master (:302-317, :286-287).  Needs rows of at
+        most 512 elements (NotImplementedError otherwise)."""
+        if len(grads) != len(self.params):
+            raise ValueError("one gradient per tensor expected")
+        for g, p in zip(grads, self.params):
+            if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == p.numel()):
+                raise ValueError("gradients must be contiguous float32 CUDA tensors matching the params")
+        if self._momentum_flat is None:
+            self._momentum_flat = torch.zeros_like(self._master_flat)
+            self.momentum_buffers, off = [], 0
+            for p in self.params:
+                self.momentum_buffers.append(self._momentum_flat[off:off + p.numel()].view(p.shape))
+                off += -(-p.numel() // 64) * 64
+            mp = (C.c_void_p * len(self.params))(*[m.data_ptr() for m in self.momentum_buffers])
+            with torch.cuda.device(self.device):
+                N.check(N.lib().qd_plan_set_momentum(self._handle, mp))
+        gp = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(self.device):
+            N.check(N.lib().qd_plan_sgd_step(self._handle, gp, _STYLE[style], float(lr), float(momentum), float(weight_decay),
+                                             1 if nesterov else 0, N.stream_ptr(self.device)))
 
     def close(self):
         if self._handle:

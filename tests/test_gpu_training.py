@@ -257,3 +257,74 @@ def test_diffquant_multi_tensor_plan_matches_per_tensor_loop(env):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (a, b)
     agree = [float((outs[0][1][k] == outs[1][1][k]).float().mean()) for k in outs[0][1] if outs[0][1][k].dtype == torch.float32]
     assert min(agree) > 0.999, min(agree)                     # a point moving by an ulp can flip a boundary element
+
+
+@pytest.mark.parametrize("style", ["none", "truncated", "complicated"])
+def test_fused_sgd_step_is_torch_sgd_then_quantize_bit_for_bit(env, style):
+    """qd_plan_sgd_step (f1, second half): gradient fix-up + torch.optim.SGD(momentum, Nesterov, weight decay)
+    + re-quantization in one pass.  Against the unfused chain -- the plan's fix-up launch, torch.optim.SGD
+    itself on the full-precision weights, uniformQuantization per tensor -- master, momentum buffer and
+    quantized weights must agree BIT FOR BIT over several steps (this pins the FMA policy of the kernel
+    to the one torch's CUDA kernels compile to)."""
+    Q, cfm, hf = env
+    from quantized_distillation_b200.plan import QuantizationPlan
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    sizes = [5000, 10, 5625, 75, 93750, 50, 800000, 500, 257, 255, 1]
+    scale = 0.6 if style == "truncated" else 0.05
+    live = [torch.randn(n, generator=gen, device="cuda") * scale for n in sizes]
+    ref_w = [torch.nn.Parameter(t.clone()) for t in live]
+    lr, mu, wd = 1e-2, 0.9, 2.2e-4
+    opt = torch.optim.SGD(ref_w, lr=lr, momentum=mu, nesterov=True, weight_decay=wd)
+    plan = QuantizationPlan(live, 16, 256)
+    ref_plan = QuantizationPlan([p.data for p in ref_w], 16, 256)       # only its fix-up launch is used, on the fp32 weights
+    if style == "truncated":
+        for t in live:
+            t.clamp_(-1, 1)
+    plan.save_and_quantize_()
+    for step in range(4):
+        grads = [torch.randn(n, generator=gen, device="cuda") for n in sizes]
+        # ---- unfused reference chain ----
+        if style == "truncated":
+            for p in ref_w:
+                p.data.clamp_(-1, 1)                                    # quantize-time clamp (:240-241)
+        rg = [g.clone() for g in grads]
+        ref_plan.backward_(rg, style)                                   # fix-up at the full-precision weights (:315)
+        for p, g in zip(ref_w, rg):
+            p.grad = g
+        opt.step()
+        if style == "truncated":
+            for p in ref_w:
+                p.data.clamp_(-1, 1)
+        # ---- fused ----
+        plan.fused_step_([g.clone() for g in grads], style, lr, mu, wd, True)
+        for i, p in enumerate(ref_w):
+            assert torch.equal(plan._master[i].view(-1), p.data.view(-1)), (style, step, i, "master")
+            buf = opt.state[p]["momentum_buffer"]
+            assert bool((plan.momentum_buffers[i].view(-1) == buf.view(-1)).all()), (style, step, i, "momentum")
+            q, _ = Q.uniformQuantization(p.data, 16, bucket_size=256)
+            assert torch.equal(live[i].view(-1), q.view(-1)), (style, step, i, "quantized")
+    with pytest.raises(NotImplementedError):
+        big = QuantizationPlan([torch.randn(4096, device="cuda")], 16, 1024)
+        big.fused_step_([torch.randn(4096, device="cuda")], "none", lr, mu, wd, True)
+
+
+@pytest.mark.parametrize("style", ["none", "complicated"])
+def test_fused_training_loop_equals_unfused(env, style):
+    """train_model(fused_optimizer_step=True) walks through the same weights as the unfused loop."""
+    Q, cfm, hf = env
+    torch.backends.cudnn.deterministic = True
+    finals = []
+    for fused in (False, True):
+        torch.manual_seed(21)
+        student = make_student(cfm)
+        teacher = make_student(cfm).eval()
+        data = hf.synthetic_cifar_loader(6, 25, seed=4)
+        model, info = cfm.train_model_quantized(student, data, data, numBits=4, bucket_size=256, use_distillation_loss=True,
+                                                teacher_model=teacher, epochs_to_train=1, print_every=3, verbose=False,
+                                                evaluate=False, backprop_quantization_style=style, fused_optimizer_step=fused,
+                                                quantize_first_and_last_layer=False)
+        assert info["fused_optimizer_step"] is fused and info["numStepsTrained"] == 6
+        finals.append([p.detach().clone() for p in model.parameters()])
+    torch.backends.cudnn.deterministic = False
+    same = [float((a == b).float().mean()) for a, b in zip(*finals)]
+    assert min(same) == 1.0, same
