@@ -193,6 +193,20 @@ int qd_plan_nonuniform_fwd(const qd_nu_plan* plan, qd_stream_t stream);
 /* grad[i]: dLoss/d(quantized tensor i), float[n[i]] */
 int qd_plan_nonuniform_bwd(const qd_nu_plan* plan, const float* const* grad, qd_stream_t stream);
 
+/* ---- next row f3: the reductions of the differentiable-quantization setup -----------------
+ * Exact order statistics without a sort: out[r] = the ranks[r]-th smallest element of v (0-based; ranks
+ * is a DEVICE array of num_ranks <= 512 entries, clamped to [0, n-1]).  This is what
+ * np.percentile(x_hat, linspace(0, 100, K)) reads (help_functions.py:140-154).  Two reads of v
+ * (value histogram, then compaction of the selected bins) plus a radix select on the compacted keys.
+ * workspace: qd_order_statistics_workspace_bytes(n) bytes. */
+size_t qd_order_statistics_workspace_bytes(int64_t n);
+int qd_order_statistics(const float* v, int64_t n, const int64_t* ranks, int num_ranks, float* out,
+                        void* workspace, size_t workspace_bytes, qd_stream_t stream);
+/* out[i] = ||tensors[i]||_2 for count tensors (host array of device pointers) in two launches, float64
+ * partial sums in a fixed order: the gradient norms of assign_bits_automatically
+ * (cnn_models/conv_forward_model.py:424-448).  Setup-time call: synchronises the stream once. */
+int qd_multi_l2norm(const float* const* tensors, const int64_t* n, int count, float* out, qd_stream_t stream);
+
 /* ---- host-buffer entry points (what a CPU-tensor caller gets) ------------
  * Inputs and outputs in HOST memory (pinned for full PCIe rate); the call
  * pipelines H2D, the fused kernel and D2H in row-aligned chunks on internal
@@ -204,7 +218,8 @@ int qd_uniform_fwd_bwd_host(const float* x_host, const float* g_host, float* q_h
 /* ---- benchmark hook: override a path-selection threshold (tools/block_bench.py measures the
  * variants against each other with it); value -1 restores the built-in choice.
  *   key 0: longest row (floats) taken by the warp-per-row two-pass variant
- *   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path */
+ *   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path
+ *   key 2: threads per CTA of the staged path (128 / 256 / 512 / 1024) */
 int qd_debug_set_tuning(int key, int64_t value);
 
 /* ---- self tests used by tests/ (device side arithmetic checks) ---------- */

@@ -52,6 +52,9 @@ SIGNATURES = {
     "qd_plan_nonuniform_destroy": (C.c_int, [_p]),
     "qd_plan_nonuniform_fwd": (C.c_int, [_p, _p]),
     "qd_plan_nonuniform_bwd": (C.c_int, [_p, _p, _p]),
+    "qd_order_statistics_workspace_bytes": (_sz, [_i64]),
+    "qd_order_statistics": (C.c_int, [_p, _i64, _p, _i32, _p, _p, _sz, _p]),
+    "qd_multi_l2norm": (C.c_int, [_p, _p, _i32, _p, _p]),
     "qd_uniform_fwd_host": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32]),
     "qd_uniform_fwd_bwd_host": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32]),
     "qd_debug_set_tuning": (C.c_int, [_i32, _i64]),

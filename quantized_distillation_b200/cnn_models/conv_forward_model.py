@@ -503,19 +503,24 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
                 break
         # ||grad / num||_2 of every selected tensor: one multi-tensor launch, one device->host copy
         sel_grads = [p.grad for p in _selected_parameters(modelToQuantize, quantize_first_and_last_layer)]
-        norms = (torch.stack(torch._foreach_norm(sel_grads)) / num_to_estimate_grad).tolist()
+        norms = (quantization.help_functions.gradient_norms(sel_grads) / num_to_estimate_grad).tolist()
         modelToQuantize.zero_grad()
         numPointsPerTensor = quantization.help_functions.assign_bits_automatically(norms, numPointsPerTensor,
                                                                                    input_is_point=True)
 
     selected = _selected_parameters(modelToQuantize, quantize_first_and_last_layer)
     pointsPerTensor = []
-    for p, num in zip(selected, numPointsPerTensor):                          # :451-482
+    # every tensor's points are a row of ONE (tensors x width) table padded with +inf, so that the
+    # per-step re-sort of all lists (:550-551) is one torch.sort instead of one per tensor
+    width = max(int(num) for num in numPointsPerTensor)
+    points_table = torch.full((len(selected), width), float("inf"), dtype=torch.float32, device=device)
+    for row, (p, num) in enumerate(zip(selected, numPointsPerTensor)):       # :451-482
         if initialize_method == "quantiles":
             init = quantization.help_functions.initialize_quantization_points(p.data, scalingFunction, num)
         else:
             init = torch.tensor([x / (num - 1) for x in range(num)], dtype=torch.float32, device=device)
-        init = init.to(device).clone().requires_grad_(True)
+        points_table[row, :num] = init.to(device)
+        init = points_table[row, :num].detach().requires_grad_(True)         # leaf tensor sharing the table's storage
         init.grad = torch.zeros_like(init)
         pointsPerTensor.append(init)
 
@@ -589,8 +594,7 @@ def optimize_quantization_points(modelToQuantize, train_loader, test_loader, ini
         for pts, gp in zip(pointsPerTensor, grads):
             pts.grad = gp
         optimizer.step()
-        for pts in pointsPerTensor:                                       # :550-551, in place: graphs hold pts' address
-            pts.data.copy_(torch.sort(pts.data)[0])
+        points_table.copy_(torch.sort(points_table, dim=1)[0])            # :550-551, every list at once, in place
         return loss, 0, 0
 
     # whole-step capture (opt-in), same mechanism as train_model(cuda_graph_step=True)

@@ -19,6 +19,7 @@
 #include "qd_grid_path.cuh"
 #include "qd_plan.cuh"
 #include "qd_points_grad.cuh"
+#include "qd_select.cuh"
 #include "qd_staged_path.cuh"
 #include "qd_warp_path.cuh"
 
@@ -185,6 +186,7 @@ static int launch_block_inst(const Params& P, cudaStream_t s) {
 // ---- tuning hook (benchmarks only): -1 = built-in choice ----------------------------------
 //   key 0: longest row (floats) handled by the warp-per-row two-pass variant of the block path
 //   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path
+//   key 2: CTA size of the staged path (128 / 256 / 512 / 1024), 0 or -1 = by row length
 static int64_t g_tune[4] = {-1, -1, -1, -1};
 extern "C" int qd_debug_set_tuning(int key, int64_t value) {
     if (key < 0 || key >= 4) return fail(QD_ERR_INVALID_ARG, "unknown tuning key %d", key);
@@ -193,12 +195,12 @@ extern "C" int qd_debug_set_tuning(int key, int64_t value) {
 }
 
 // CTA per row, TMA chunk ring (qd_staged_path.cuh)
-template <int OP, int BWD, int STAGES>
+template <int OP, int BWD, int STAGES, int T>
 static int launch_staged_inst(const Params& P, cudaStream_t s) {
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    auto kern = staged_rows_kernel<OP, BWD, STAGES>;
+    auto kern = staged_rows_kernel<OP, BWD, STAGES, T>;
     const int stage_floats = (int)((P.geo.row_len + 31) & ~(int64_t)31);
     const size_t smem = (size_t)STAGES * stage_floats * sizeof(float);
     if (smem + 8192 > di->smem_optin) return fail(QD_ERR_UNSUPPORTED, "row of %lld floats does not fit in shared memory", (long long)P.geo.row_len);
@@ -209,26 +211,40 @@ static int launch_staged_inst(const Params& P, cudaStream_t s) {
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         opted[d & 63] = smem;
     }
-    const int occ = resident_ctas(kern, kBlockCtaThreads, smem);
+    const int occ = resident_ctas(kern, T, smem);
     const int64_t cap = (int64_t)di->sms * occ;
     const int grid = (int)(P.geo.rows < cap ? P.geo.rows : cap);
-    kern<<<grid, kBlockCtaThreads, smem, s>>>(P, stage_floats);
+    kern<<<grid, T, smem, s>>>(P, stage_floats);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
 
+// CTA size and ring depth by row length; measured on B200 (tools/block_bench.py, profiles/block_path_r2.md).
+// g_tune[1] = longest row with two rows in flight per CTA, g_tune[2] = forced CTA size.
+template <int OP, int BWD>
+static int launch_staged(const Params& P, cudaStream_t s) {
+    const int64_t L = P.geo.row_len;
+    const int64_t two_max = g_tune[1] >= 0 ? g_tune[1] : kTwoStageMaxRow;
+    const bool two = L <= two_max && L <= 24576;
+    int T = L <= 2048 ? 128 : L <= 8192 ? 256 : L <= 24576 ? 512 : 1024;
+    if (g_tune[2] > 0) T = (int)g_tune[2];
+    if (two) {
+        if (T <= 128) return launch_staged_inst<OP, BWD, 2, 128>(P, s);
+        if (T <= 256) return launch_staged_inst<OP, BWD, 2, 256>(P, s);
+        return launch_staged_inst<OP, BWD, 2, 512>(P, s);
+    }
+    if (T <= 256) return launch_staged_inst<OP, BWD, 1, 256>(P, s);
+    if (T <= 512) return launch_staged_inst<OP, BWD, 1, 512>(P, s);
+    return launch_staged_inst<OP, BWD, 1, 1024>(P, s);
+}
+
 template <int OP, int BWD>
 static int launch_block(const Params& P, cudaStream_t s) {
-    // measured on B200 (tools/block_bench.py): see profiles/block_path_r2.txt
     const int64_t warp2_default = (BWD == (int)BWD_MINMAX) ? kWarpTwoPassMaxRow : 2 * kWarpTwoPassMaxRow;
     const int64_t warp2_max = g_tune[0] >= 0 ? g_tune[0] : warp2_default;
     if (P.geo.row_len <= warp2_max) return launch_block_inst<OP, BWD, false, 32>(P, s);               // warp per row, two passes
     if constexpr (OP == OP_UNIFORM || OP == OP_NONUNIFORM) {
-        if (!P.stochastic) {
-            const int64_t two_max = g_tune[1] >= 0 ? g_tune[1] : kTwoStageMaxRow;
-            if (P.geo.row_len <= two_max && P.geo.row_len <= 24576) return launch_staged_inst<OP, BWD, 2>(P, s);
-            return launch_staged_inst<OP, BWD, 1>(P, s);
-        }
+        if (!P.stochastic) return launch_staged<OP, BWD>(P, s);
     }
     return launch_block_inst<OP, BWD, true, kBlockCtaThreads>(P, s);  // scale / stats / stochastic: CTA per row, whole-row staging
 }
@@ -977,6 +993,69 @@ extern "C" int qd_plan_nonuniform_bwd(const qd_nu_plan* p, const float* const* g
     QD_CUDA(cudaGetLastError());
     plan_points_grad_final<<<(p->count + 7) / 8, 256, 0, s>>>(p->dev, p->count, p->partial);
     QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+// ------------------------------------------------------------------ f3: order statistics / multi-tensor norms
+static size_t select_header_bytes() {
+    size_t h = sizeof(unsigned long long) * kSelBins + sizeof(SelectState);
+    return (h + 255) & ~(size_t)255;
+}
+extern "C" size_t qd_order_statistics_workspace_bytes(int64_t n) {
+    return n > 0 ? select_header_bytes() + (size_t)n * sizeof(uint32_t) : 0;
+}
+
+extern "C" int qd_order_statistics(const float* v, int64_t n, const int64_t* ranks, int num_ranks, float* out,
+                                   void* workspace, size_t workspace_bytes, qd_stream_t stream) {
+    if (v == nullptr || ranks == nullptr || out == nullptr || n <= 0) return fail(QD_ERR_INVALID_ARG, "NULL argument or n <= 0");
+    if (num_ranks < 1 || num_ranks > kSelMaxRanks) return fail(QD_ERR_INVALID_ARG, "num_ranks must be in [1, %d]", kSelMaxRanks);
+    if (workspace == nullptr || workspace_bytes < qd_order_statistics_workspace_bytes(n))
+        return fail(QD_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", qd_order_statistics_workspace_bytes(n), workspace_bytes);
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(workspace);
+    SelectState* st = reinterpret_cast<SelectState*>(hist + kSelBins);
+    uint32_t* buf = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + select_header_bytes());
+    QD_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * kSelBins, s));
+    const int64_t need = (n / 4 + kSelThreads - 1) / kSelThreads + 1;
+    const int grid = (int)(need < (int64_t)di->sms * 4 ? need : (int64_t)di->sms * 4);
+    select_hist_kernel<<<grid, kSelThreads, 0, s>>>(v, n, hist);
+    select_plan_kernel<<<1, kSelThreads, 0, s>>>(hist, ranks, num_ranks, st);
+    select_compact_kernel<<<grid, kSelThreads, 0, s>>>(v, n, st, buf);
+    select_final_kernel<<<num_ranks, kSelThreads, 0, s>>>(st, buf, out);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_multi_l2norm(const float* const* tensors, const int64_t* n, int count, float* out, qd_stream_t stream) {
+    if (tensors == nullptr || n == nullptr || out == nullptr || count <= 0) return fail(QD_ERR_INVALID_ARG, "bad arguments");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    std::vector<NormEntry> host(count);
+    int64_t chunks = 0;
+    for (int i = 0; i < count; ++i) {
+        if (tensors[i] == nullptr || n[i] <= 0) return fail(QD_ERR_INVALID_ARG, "bad tensor %d", i);
+        host[i].ptr = tensors[i]; host[i].n = n[i]; host[i].chunk_start = chunks;
+        host[i].chunks = (n[i] + kNormChunk - 1) / kNormChunk;
+        chunks += host[i].chunks;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    NormEntry* dev = nullptr;
+    double* partial = nullptr;
+    // setup-time call (once per bit allocation): stream-ordered scratch, table copied before the launch
+    QD_CUDA(cudaMallocAsync(&dev, sizeof(NormEntry) * count, s));
+    QD_CUDA(cudaMallocAsync(&partial, sizeof(double) * (size_t)chunks, s));
+    QD_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(NormEntry) * count, cudaMemcpyHostToDevice, s));
+    QD_CUDA(cudaStreamSynchronize(s));   // `host` goes out of scope; this entry point is not on the per-step path
+    const int64_t cap = (int64_t)di->sms * 8;
+    multi_norm_partial<<<(int)(chunks < cap ? chunks : cap), 256, 0, s>>>(dev, count, chunks, partial);
+    multi_norm_final<<<(count + 255) / 256, 256, 0, s>>>(dev, count, partial, out);
+    QD_CUDA(cudaGetLastError());
+    QD_CUDA(cudaFreeAsync(dev, s));
+    QD_CUDA(cudaFreeAsync(partial, s));
     return QD_OK;
 }
 

@@ -21,6 +21,8 @@
 // elements of the gradient change (first argmax' / argmin' of q), so sweep 2 streams g once, writes
 // gout = g, accumulates r_b and the two positions, and thread 0 patches the two elements afterwards.
 #pragma once
+#include <type_traits>
+
 #include "qd_block_path.cuh"
 
 namespace qd {
@@ -28,21 +30,23 @@ namespace qd {
 constexpr int kTwoStageMaxRow = 8192;  // floats; rows up to here keep two rows in flight per CTA
 
 struct StagedScratch {
-    float mm[2][2][kBlockCtaThreads / 32];  // [exchange parity][min | max][warp]
-    int im[2][2][kBlockCtaThreads / 32];    // first positions
-    double acc[2][kBlockCtaThreads / 32];   // r_b partials
+    float mm[2][2][32];  // [exchange parity][min | max][warp]
+    int im[2][2][32];    // first positions
+    double acc[2][32];   // r_b partials
 };
 
-template <int OP, int BWD, int STAGES>
-// two resident CTAs per SM (<= 64 registers): short rows overlap each other's phases
-__global__ void __launch_bounds__(kBlockCtaThreads, 2) staged_rows_kernel(const __grid_constant__ Params P, int stage_floats) {
+// T threads per CTA, chosen by row length (qd_api.cu): short rows want MANY small CTAs per SM (cheap
+// barriers, many rows in flight), rows that fill the shared memory of an SM want one large CTA (all
+// the warps the SM can hold).  Registers are capped at 64 so that 2048 / T CTAs fit.
+template <int OP, int BWD, int STAGES, int T>
+__global__ void __launch_bounds__(T, T == 128 ? 8 : T == 256 ? 4 : T == 512 ? 2 : 1)
+staged_rows_kernel(const __grid_constant__ Params P, int stage_floats) {
     static_assert(OP == OP_UNIFORM || OP == OP_NONUNIFORM, "staged path: deterministic uniform / centroid op");
     extern __shared__ __align__(128) float s_dyn[];
     __shared__ __align__(8) uint64_t s_bar[STAGES][kMaxStageChunks];
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
     __shared__ float s_t[OP == OP_NONUNIFORM ? 256 : 1];
     __shared__ StagedScratch sc;
-    constexpr int T = kBlockCtaThreads;
     constexpr int NW = T / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -86,10 +90,6 @@ __global__ void __launch_bounds__(kBlockCtaThreads, 2) staged_rows_kernel(const 
         for (int s = 0; s < STAGES; ++s)
             for (int c = 0; c < kMaxStageChunks; ++c) issue_chunk(s, c);
     }
-
-    LaneSearch<32> ls;  // centroid tables of up to 32 points live in the lanes
-    const bool lanes_ok = OP == OP_NONUNIFORM && P.num_points <= 32;
-    if constexpr (OP == OP_NONUNIFORM) ls.load(cen, lane);
 
     for (int64_t it = 0;; ++it) {
         const int64_t row = (int64_t)blockIdx.x + it * gridDim.x;
@@ -205,57 +205,86 @@ __global__ void __launch_bounds__(kBlockCtaThreads, 2) staged_rows_kernel(const 
                 rs.alpha2 = make_alpha(qlo, qhi);
                 div2 = RowDivider(rs.alpha2);
             }
-            auto bwd_elem = [&](int e, float xv, float qv, float gv) -> float {
-                if constexpr (BWD == BWD_TRUNC) gv = (fabsf(xv) > 1.0f) ? 0.f : gv;
-                if constexpr (BWD == BWD_MINMAX) {
-                    if (qv == qlo) imin2 = min(imin2, e);
-                    if (qv == qhi) imax2 = min(imax2, e);
-                    acc += (double)minmax_term(xv, qv, gv, rs.beta2, div2);
-                }
-                return gv;
-            };
-            for (int c = 0; c < sweep_chunks; ++c) {
-                int lo, hi;
-                chunk_range(c, lo, hi);
+            // FASTDIV: the row's alpha' lets both divisions of the min/max term use the hoisted reciprocal
+            // (row-uniform, so the test is made once per row instead of twice per element)
+            auto sweep = [&](auto fast_tag) {
+                constexpr bool FASTDIV = decltype(fast_tag)::value;
+                auto term = [&](float xv, float qv, float gv) -> float {
+                    const float qh = FASTDIV ? div2.fast(__fsub_rn(qv, rs.beta2)) : RowDivider::slow_div(__fsub_rn(qv, rs.beta2), rs.alpha2);
+                    const float xs = FASTDIV ? div2.fast(__fsub_rn(xv, rs.beta2)) : RowDivider::slow_div(__fsub_rn(xv, rs.beta2), rs.alpha2);
+                    return __fmul_rn(gv, __fsub_rn(qh, xs));   // v_j = g_j (q_hat_j - x_hat_j)  (quant_functions.py:400)
+                };
+                for (int c = 0; c < sweep_chunks; ++c) {
+                    int lo, hi;
+                    chunk_range(c, lo, hi);
 #pragma unroll 2
-                for (int e = lo + tid * 4; e < hi; e += T * 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(buf + e);
-                    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if constexpr (BWD != BWD_OFF) {
-                        gv = ovec ? ld_hint4(P.g + base + e, pol_stream)
-                                  : make_float4(P.g[base + e], P.g[base + e + 1], P.g[base + e + 2], P.g[base + e + 3]);
+                    for (int e = lo + tid * 4; e < hi; e += T * 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(buf + e);
+                        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if constexpr (BWD != BWD_OFF) {
+                            gv = ovec ? ld_hint4(P.g + base + e, pol_stream)
+                                      : make_float4(P.g[base + e], P.g[base + e + 1], P.g[base + e + 2], P.g[base + e + 3]);
+                        }
+                        float lv[4];
+                        float4 qo = uniform_quantize_auto4(t, rs.alpha, rs.beta, uf, P.S, P.rS, P.half_minus_band, lv);
+                        if constexpr (BWD == BWD_TRUNC) {
+                            gv.x = (fabsf(t.x) > 1.0f) ? 0.f : gv.x; gv.y = (fabsf(t.y) > 1.0f) ? 0.f : gv.y;
+                            gv.z = (fabsf(t.z) > 1.0f) ? 0.f : gv.z; gv.w = (fabsf(t.w) > 1.0f) ? 0.f : gv.w;
+                        }
+                        if constexpr (BWD == BWD_MINMAX) {
+                            if (qo.x == qlo) imin2 = min(imin2, e);
+                            if (qo.y == qlo) imin2 = min(imin2, e + 1);
+                            if (qo.z == qlo) imin2 = min(imin2, e + 2);
+                            if (qo.w == qlo) imin2 = min(imin2, e + 3);
+                            if (qo.x == qhi) imax2 = min(imax2, e);
+                            if (qo.y == qhi) imax2 = min(imax2, e + 1);
+                            if (qo.z == qhi) imax2 = min(imax2, e + 2);
+                            if (qo.w == qhi) imax2 = min(imax2, e + 3);
+                            // four float32 terms are added in float32 (three roundings of ~6e-8 relative, far inside the
+                            // 1e-6 budget of the float32-vs-float64 summation order), then the group joins the float64 sum
+                            const float v4 = __fadd_rn(__fadd_rn(term(t.x, qo.x, gv.x), term(t.y, qo.y, gv.y)),
+                                                       __fadd_rn(term(t.z, qo.z, gv.z), term(t.w, qo.w, gv.w)));
+                            acc += (double)v4;
+                        }
+                        if constexpr (BWD != BWD_OFF) {
+                            if (ovec) st_hint4(P.gout + base + e, gv, pol_stream);
+                            else { P.gout[base + e] = gv.x; P.gout[base + e + 1] = gv.y; P.gout[base + e + 2] = gv.z; P.gout[base + e + 3] = gv.w; }
+                        }
+                        if (P.q != nullptr) {
+                            if (pre) { qo.x = __fadd_rn(qo.x, mean); qo.y = __fadd_rn(qo.y, mean); qo.z = __fadd_rn(qo.z, mean); qo.w = __fadd_rn(qo.w, mean); }
+                            if (ovec) st_hint4(P.q + base + e, qo, pol_stream);
+                            else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
+                        }
+                        if (P.idx8 != nullptr) {
+                            if (ovec) *reinterpret_cast<uint32_t*>(P.idx8 + base + e) =
+                                    (uint32_t)(int)lv[0] | ((uint32_t)(int)lv[1] << 8) | ((uint32_t)(int)lv[2] << 16) | ((uint32_t)(int)lv[3] << 24);
+                            else for (int j = 0; j < 4; ++j) P.idx8[base + e + j] = (uint8_t)(int)lv[j];
+                        }
                     }
-                    float lv[4];
-                    float4 qo = uniform_quantize_auto4(t, rs.alpha, rs.beta, uf, P.S, P.rS, P.half_minus_band, lv);
-                    if constexpr (BWD != BWD_OFF) {
-                        gv.x = bwd_elem(e, t.x, qo.x, gv.x); gv.y = bwd_elem(e + 1, t.y, qo.y, gv.y);
-                        gv.z = bwd_elem(e + 2, t.z, qo.z, gv.z); gv.w = bwd_elem(e + 3, t.w, qo.w, gv.w);
-                        if (ovec) st_hint4(P.gout + base + e, gv, pol_stream);
-                        else { P.gout[base + e] = gv.x; P.gout[base + e + 1] = gv.y; P.gout[base + e + 2] = gv.z; P.gout[base + e + 3] = gv.w; }
+                    if (c == sweep_chunks - 1) {
+                        for (int e = len4 + tid; e < len; e += T) {  // scalar tail of the row
+                            const float t = buf[e];
+                            float lvl;
+                            const float qv = uniform_quantize_auto(t, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
+                            if constexpr (BWD != BWD_OFF) {
+                                float gv = P.g[base + e];
+                                if constexpr (BWD == BWD_TRUNC) gv = (fabsf(t) > 1.0f) ? 0.f : gv;
+                                if constexpr (BWD == BWD_MINMAX) {
+                                    if (qv == qlo) imin2 = min(imin2, e);
+                                    if (qv == qhi) imax2 = min(imax2, e);
+                                    acc += (double)term(t, qv, gv);
+                                }
+                                P.gout[base + e] = gv;
+                            }
+                            if (P.q != nullptr) P.q[base + e] = pre ? __fadd_rn(qv, mean) : qv;
+                            if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)(int)lvl;
+                        }
                     }
-                    if (P.q != nullptr) {
-                        if (pre) { qo.x = __fadd_rn(qo.x, mean); qo.y = __fadd_rn(qo.y, mean); qo.z = __fadd_rn(qo.z, mean); qo.w = __fadd_rn(qo.w, mean); }
-                        if (ovec) st_hint4(P.q + base + e, qo, pol_stream);
-                        else { P.q[base + e] = qo.x; P.q[base + e + 1] = qo.y; P.q[base + e + 2] = qo.z; P.q[base + e + 3] = qo.w; }
-                    }
-                    if (P.idx8 != nullptr) {
-                        if (ovec) *reinterpret_cast<uint32_t*>(P.idx8 + base + e) =
-                                (uint32_t)(int)lv[0] | ((uint32_t)(int)lv[1] << 8) | ((uint32_t)(int)lv[2] << 16) | ((uint32_t)(int)lv[3] << 24);
-                        else for (int j = 0; j < 4; ++j) P.idx8[base + e + j] = (uint8_t)(int)lv[j];
-                    }
+                    if (BWD != BWD_MINMAX || c + 1 < sweep_chunks) chunk_done(c);
                 }
-                if (c == sweep_chunks - 1) {
-                    for (int e = len4 + tid; e < len; e += T) {  // scalar tail of the row
-                        const float t = buf[e];
-                        float lvl;
-                        float qv = uniform_quantize_auto(t, rs, uf, P.S, P.rS, P.half_minus_band, lvl);
-                        if constexpr (BWD != BWD_OFF) P.gout[base + e] = bwd_elem(e, t, qv, P.g[base + e]);
-                        if (P.q != nullptr) P.q[base + e] = pre ? __fadd_rn(qv, mean) : qv;
-                        if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)(int)lvl;
-                    }
-                }
-                if (BWD != BWD_MINMAX || c + 1 < sweep_chunks) chunk_done(c);
-            }
+            };
+            if (BWD == BWD_MINMAX && div2.ok) sweep(std::true_type{});
+            else sweep(std::false_type{});
             if constexpr (BWD == BWD_MINMAX) {
                 // r_b and the two positions: fixed reduction tree (lanes, then warps in order) -> deterministic
                 acc = warp_sum(acc);
@@ -281,71 +310,84 @@ __global__ void __launch_bounds__(kBlockCtaThreads, 2) staged_rows_kernel(const 
         } else {  // OP_NONUNIFORM
             const RowDivider div(rs.alpha);
             const unsigned thr_bits = __float_as_uint(div.thr()) - 1u;
-            const float q_lane = ls.row_table(rs.alpha, rs.beta, pre, mean);
-            for (int c = 0; c < sweep_chunks; ++c) {
-                int lo, hi;
-                chunk_range(c, lo, hi);
-                // warp-uniform trip count (the lane search shuffles): a warp owns 128 consecutive floats per step
-                for (int e0 = lo + warp * 128; e0 < hi; e0 += T * 4) {
-                    const int e = e0 + lane * 4;
-                    const bool act = e < hi;
-                    const float4 t = act ? *reinterpret_cast<const float4*>(buf + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float a[4] = {__fsub_rn(t.x, rs.beta), __fsub_rn(t.y, rs.beta), __fsub_rn(t.z, rs.beta), __fsub_rn(t.w, rs.beta)};
-                    float xh[4];
-                    unsigned guard = 0xffffffffu;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        xh[j] = div.fast(a[j]);
-                        guard = RowDivider::guard_fold(guard, a[j]);
-                    }
-                    if (!div.ok || guard < thr_bits) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) xh[j] = RowDivider::slow_div(a[j], rs.alpha);
-                    }
-                    float qq[4];
-                    int ii[4];
-                    if (lanes_ok) {
+            // KP: size class of the lane table (compile time inside the sweep, chosen once per launch)
+            auto sweep = [&](auto kp_tag) {
+                constexpr int KP = decltype(kp_tag)::value;
+                constexpr bool LANES = KP <= 32;
+                LaneSearch<LANES ? KP : 1> ls;
+                float q_lane = 0.f;
+                if constexpr (LANES) {
+                    ls.load(cen, lane);
+                    q_lane = ls.row_table(rs.alpha, rs.beta, pre, mean);
+                }
+                for (int c = 0; c < sweep_chunks; ++c) {
+                    int lo, hi;
+                    chunk_range(c, lo, hi);
+                    // warp-uniform trip count (the lane search shuffles): a warp owns 128 consecutive floats per step
+                    for (int e0 = lo + warp * 128; e0 < hi; e0 += T * 4) {
+                        const int e = e0 + lane * 4;
+                        const bool act = e < hi;
+                        const float4 t = act ? *reinterpret_cast<const float4*>(buf + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float a[4] = {__fsub_rn(t.x, rs.beta), __fsub_rn(t.y, rs.beta), __fsub_rn(t.z, rs.beta), __fsub_rn(t.w, rs.beta)};
+                        float xh[4];
+                        unsigned guard = 0xffffffffu;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            ii[j] = ls.index(xh[j]);
-                            qq[j] = LaneSearch<32>::value(q_lane, ii[j]);
+                            xh[j] = div.fast(a[j]);
+                            guard = RowDivider::guard_fold(guard, a[j]);
                         }
-                    } else {
+                        if (!div.ok || guard < thr_bits) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) xh[j] = RowDivider::slow_div(a[j], rs.alpha);
+                        }
+                        float qq[4];
+                        int ii[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            if constexpr (LANES) {
+                                ii[j] = ls.index(xh[j]);
+                                qq[j] = LaneSearch<LANES ? KP : 1>::value(q_lane, ii[j]);
+                            } else {
+                                float kval;
+                                ii[j] = smem_index<256>(cen.k, cen.t, xh[j], kval);
+                                qq[j] = from_unit(kval, rs.alpha, rs.beta);
+                                if (pre) qq[j] = __fadd_rn(qq[j], mean);
+                            }
+                        }
+                        if (act) {
+                            if (P.q != nullptr) {
+                                if (ovec) st_hint4(P.q + base + e, make_float4(qq[0], qq[1], qq[2], qq[3]), pol_stream);
+                                else { P.q[base + e] = qq[0]; P.q[base + e + 1] = qq[1]; P.q[base + e + 2] = qq[2]; P.q[base + e + 3] = qq[3]; }
+                            }
+                            if (P.idx8 != nullptr) {
+                                if (ovec) *reinterpret_cast<uint32_t*>(P.idx8 + base + e) =
+                                        (uint32_t)ii[0] | ((uint32_t)ii[1] << 8) | ((uint32_t)ii[2] << 16) | ((uint32_t)ii[3] << 24);
+                                else { P.idx8[base + e] = (uint8_t)ii[0]; P.idx8[base + e + 1] = (uint8_t)ii[1]; P.idx8[base + e + 2] = (uint8_t)ii[2]; P.idx8[base + e + 3] = (uint8_t)ii[3]; }
+                            }
+                            if (P.idx64 != nullptr) { P.idx64[base + e] = ii[0]; P.idx64[base + e + 1] = ii[1]; P.idx64[base + e + 2] = ii[2]; P.idx64[base + e + 3] = ii[3]; }
+                        }
+                    }
+                    if (c == sweep_chunks - 1) {
+                        for (int e = len4 + tid; e < len; e += T) {  // scalar tail: table search in shared memory
+                            const float xh = div.exact(__fsub_rn(buf[e], rs.beta));
                             float kval;
-                            ii[j] = smem_index<256>(cen.k, cen.t, xh[j], kval);
-                            qq[j] = from_unit(kval, rs.alpha, rs.beta);
-                            if (pre) qq[j] = __fadd_rn(qq[j], mean);
+                            const int id = smem_index<256>(cen.k, cen.t, xh, kval);
+                            float qv = from_unit(kval, rs.alpha, rs.beta);
+                            if (pre) qv = __fadd_rn(qv, mean);
+                            if (P.q != nullptr) P.q[base + e] = qv;
+                            if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)id;
+                            if (P.idx64 != nullptr) P.idx64[base + e] = id;
                         }
                     }
-                    if (act) {
-                        if (P.q != nullptr) {
-                            if (ovec) st_hint4(P.q + base + e, make_float4(qq[0], qq[1], qq[2], qq[3]), pol_stream);
-                            else { P.q[base + e] = qq[0]; P.q[base + e + 1] = qq[1]; P.q[base + e + 2] = qq[2]; P.q[base + e + 3] = qq[3]; }
-                        }
-                        if (P.idx8 != nullptr) {
-                            if (ovec) *reinterpret_cast<uint32_t*>(P.idx8 + base + e) =
-                                    (uint32_t)ii[0] | ((uint32_t)ii[1] << 8) | ((uint32_t)ii[2] << 16) | ((uint32_t)ii[3] << 24);
-                            else { P.idx8[base + e] = (uint8_t)ii[0]; P.idx8[base + e + 1] = (uint8_t)ii[1]; P.idx8[base + e + 2] = (uint8_t)ii[2]; P.idx8[base + e + 3] = (uint8_t)ii[3]; }
-                        }
-                        if (P.idx64 != nullptr) { P.idx64[base + e] = ii[0]; P.idx64[base + e + 1] = ii[1]; P.idx64[base + e + 2] = ii[2]; P.idx64[base + e + 3] = ii[3]; }
-                    }
+                    chunk_done(c);
                 }
-                if (c == sweep_chunks - 1) {
-                    for (int e = len4 + tid; e < len; e += T) {  // scalar tail: table search in shared memory
-                        const float xh = div.exact(__fsub_rn(buf[e], rs.beta));
-                        float kval;
-                        const int id = smem_index<256>(cen.k, cen.t, xh, kval);
-                        float qv = from_unit(kval, rs.alpha, rs.beta);
-                        if (pre) qv = __fadd_rn(qv, mean);
-                        if (P.q != nullptr) P.q[base + e] = qv;
-                        if (P.idx8 != nullptr) P.idx8[base + e] = (uint8_t)id;
-                        if (P.idx64 != nullptr) P.idx64[base + e] = id;
-                    }
-                }
-                chunk_done(c);
-            }
+            };
+            const int K = P.num_points;
+            if (K <= 4) sweep(std::integral_constant<int, 4>{});
+            else if (K <= 8) sweep(std::integral_constant<int, 8>{});
+            else if (K <= 16) sweep(std::integral_constant<int, 16>{});
+            else if (K <= 32) sweep(std::integral_constant<int, 32>{});
+            else sweep(std::integral_constant<int, 256>{});
         }
     }
 }

@@ -14,7 +14,7 @@ import torch
 from .. import _native as N
 
 __all__ = ("create_bucket_tensor", "assign_bits_automatically", "initialize_quantization_points", "huffman_encode",
-           "get_huffman_encoding_mean_bit_length", "index_histogram")
+           "get_huffman_encoding_mean_bit_length", "index_histogram", "order_statistics", "gradient_norms")
 
 
 def create_bucket_tensor(tensor, bucket_size, fill_values="last"):
@@ -90,22 +90,49 @@ def percentile_combine(prev_vals: np.ndarray, next_vals: np.ndarray, gamma: np.n
 
 def initialize_quantization_points(tensor, scaling_function, num_points):
     """Percentile initialisation of the centroids on the scaled tensor
-    (reference: help_functions.py:140-154).  The scaling and a sort run on the
-    GPU; only the 2K order statistics numpy's percentile would read are brought
-    to the host and combined with numpy's own interpolation, so the result is
-    bit-identical to ``np.percentile`` over the whole array."""
+    (reference: help_functions.py:140-154).  The scaling runs on the GPU and the 2K order
+    statistics numpy's percentile would read are SELECTED there (qd_order_statistics: value
+    histogram + compaction + radix select, no sort); only those 2K floats come to the host,
+    where they are combined with numpy's interpolation formula, so the result is bit-identical
+    to ``np.percentile`` over the whole array."""
     scaled = scaling_function.scale_down(tensor).view(-1)[0:scaling_function.original_tensor_length]
     n = scaled.numel()
     if not scaled.is_cuda:
         N.require_cuda()
         scaled = scaled.cuda()
-    ordered = torch.sort(scaled)[0]
     prev, nxt, gamma = percentile_plan(n, num_points)
-    sel = torch.from_numpy(np.concatenate([prev, nxt]).astype(np.int64)).to(ordered.device)
-    picks = ordered[sel].cpu().numpy()
+    picks = order_statistics(scaled, np.concatenate([prev, nxt])).cpu().numpy()
     initial_points = percentile_combine(picks[:num_points], picks[num_points:], gamma)
     initial_points = torch.from_numpy(np.asarray(initial_points)).type_as(tensor)
     return initial_points.to(tensor.device)
+
+
+def order_statistics(values: torch.Tensor, ranks) -> torch.Tensor:
+    """The ``ranks``-th smallest elements (0-based) of a float32 CUDA tensor, exactly, without
+    sorting it (qd_order_statistics).  At most 512 ranks per call."""
+    N.require_cuda()
+    values = values.contiguous().view(-1)
+    ranks_t = torch.as_tensor(np.asarray(ranks, dtype=np.int64)).to(values.device)
+    out = torch.empty(ranks_t.numel(), dtype=torch.float32, device=values.device)
+    ws_bytes = int(N.lib().qd_order_statistics_workspace_bytes(values.numel()))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=values.device)
+    N.check(N.lib().qd_order_statistics(N.ptr(values), values.numel(), N.ptr(ranks_t), ranks_t.numel(), N.ptr(out),
+                                        N.ptr(ws), ws_bytes, N.stream_ptr(values.device)))
+    return out
+
+
+def gradient_norms(tensors):
+    """L2 norm of every tensor of a list in two launches (qd_multi_l2norm), as a float32 CUDA tensor."""
+    import ctypes as C
+    N.require_cuda()
+    tensors = [t.contiguous() for t in tensors]
+    dev = tensors[0].device
+    out = torch.empty(len(tensors), dtype=torch.float32, device=dev)
+    ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    ns = (C.c_int64 * len(tensors))(*[t.numel() for t in tensors])
+    with torch.cuda.device(dev):
+        N.check(N.lib().qd_multi_l2norm(ptrs, ns, len(tensors), N.ptr(out), N.stream_ptr(dev)))
+    return out
 
 
 def huffman_encode(symb2freq):

@@ -609,10 +609,11 @@ def test_centroid_plan_matches_per_tensor_ops_and_oracle(Q):
         a = [g.clone() for g in plan.backward_([dev(g) for g in gs])]
         b = [g.clone() for g in plan.backward_([dev(g) for g in gs])]
         assert all(torch.equal(u, v) for u, v in zip(a, b))
-    with pytest.raises(NotImplementedError):
-        CentroidPlan([dev(xs[0])], [torch.empty(len(xs[0]), device="cuda")], [torch.linspace(0, 1, 33, device="cuda")], 256)
-    with pytest.raises(NotImplementedError):
-        CentroidPlan([dev(xs[0])], [torch.empty(len(xs[0]), device="cuda")], [torch.linspace(0, 1, 4, device="cuda")], 2048)
+    big = torch.randn(5000, device="cuda")
+    with pytest.raises(NotImplementedError):                    # more than 32 points
+        CentroidPlan([big], [torch.empty_like(big)], [torch.linspace(0, 1, 33, device="cuda")], 256)
+    with pytest.raises(NotImplementedError):                    # rows longer than 1024 elements
+        CentroidPlan([big], [torch.empty_like(big)], [torch.linspace(0, 1, 4, device="cuda")], 2048)
 
 
 def test_error_mapping(Q):

@@ -62,15 +62,22 @@ def main():
             "nonuniform_K4_mid": (9, lambda: N.check(lib.qd_nonuniform_fwd(N.ptr(x), N.ptr(pts4), 4, N.RULE_MIDPOINT, N.ptr(q), N.ptr(idx), None, None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp))),
             "nonuniform_K16_near": (9, lambda: N.check(lib.qd_nonuniform_fwd(N.ptr(x), N.ptr(pts16), 16, N.RULE_NEAREST, N.ptr(q), N.ptr(idx), None, None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp))),
         }
-        variants = {"auto": (-1, -1)}
+        # variant -> (key 0 warp2_max, key 1 two_stage_max, key 2 threads per CTA)
+        variants = {"auto": (-1, -1, -1)}
         if bucket <= 8192:
-            variants["warp2"] = (1 << 20, -1)
-        if bucket <= 24576:
-            variants["staged2"] = (0, 1 << 20)
-        variants["staged1"] = (0, 0)
-        for vname, (t0, t1) in variants.items():
+            variants["warp2"] = (1 << 20, -1, -1)
+        for stages, threads in ((2, 128), (2, 256), (2, 512), (1, 256), (1, 512), (1, 1024)):
+            if stages == 2 and bucket > 24576:
+                continue
+            if threads == 128 and bucket > 4096 or threads == 256 and bucket > 16384 or threads == 1024 and bucket < 8192:
+                continue
+            if stages == 1 and bucket < 4096:
+                continue
+            variants[f"s{stages}t{threads}"] = (0, (1 << 20) if stages == 2 else 0, threads)
+        for vname, (t0, t1, t2) in variants.items():
             tune(0, t0)
             tune(1, t1)
+            tune(2, t2)
             for oname, (bpe, fn) in ops.items():
                 if vname == "warp2" and oname == "uniform_fwd" and bucket <= 2048:
                     continue          # the plain forward keeps rows <= 2048 in registers (warp path), not a block variant
@@ -78,12 +85,11 @@ def main():
                 gbs = n * bpe / sec / 1e9
                 rows.append({"bucket": bucket, "variant": vname, "op": oname, "us": round(sec * 1e6, 1), "GBps": round(gbs, 1),
                              "frac_measured_peak": round(gbs / peak, 3)})
+        tune(2, -1)
         tune(0, -1)
         tune(1, -1)
-        line = f"bucket {bucket:6d}: " + " | ".join(
-            f"{o} " + "/".join(f"{v[:3]}{r['us']:.0f}" for r in rows if r["bucket"] == bucket and r["op"] == o for v in [r["variant"]])
-            for o in ops)
-        print(line, flush=True)
+        print(f"bucket {bucket:6d}: " + " | ".join(
+            f"{o} " + "/".join(f"{r['variant']}={r['us']:.0f}" for r in rows if r["bucket"] == bucket and r["op"] == o) for o in ops), flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump({"n": n, "peak_GBps": peak, "rows": rows}, f, indent=1)
@@ -92,7 +98,7 @@ def main():
         opn = list(dict.fromkeys(r["op"] for r in rows))
         f.write("| bucket | variant | " + " | ".join(opn) + " |\n|---|---|" + "---|" * len(opn) + "\n")
         for b in buckets:
-            for v in ("auto", "warp2", "staged2", "staged1"):
+            for v in list(dict.fromkeys(r["variant"] for r in rows)):
                 cells = []
                 for o in opn:
                     m = [r for r in rows if r["bucket"] == b and r["variant"] == v and r["op"] == o]
