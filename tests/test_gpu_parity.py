@@ -616,6 +616,41 @@ def test_centroid_plan_matches_per_tensor_ops_and_oracle(Q):
         CentroidPlan([big], [torch.empty_like(big)], [torch.linspace(0, 1, 4, device="cuda")], 2048)
 
 
+def test_order_statistics_select_is_exact(Q):
+    """qd_order_statistics (value histogram + compaction + radix select) against a full sort, bit for
+    bit: uniform / peaked / constant / heavy-tie inputs, values outside [0, 1], tiny tensors, up to 512
+    ranks, unaligned views."""
+    from quantized_distillation_b200.quantization import help_functions as H
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    cases = []
+    for n in (1, 2, 5, 257, 4099, 100003, 5_000_017):
+        cases.append(torch.rand(n, generator=gen, device="cuda"))
+        cases.append((torch.randn(n, generator=gen, device="cuda") * 0.02 + 0.5).clamp_(0, 1))      # peaked: few value bins hold everything
+    cases.append(torch.full((70001,), 0.25, device="cuda"))
+    cases.append(torch.randint(0, 4, (300000,), generator=gen, device="cuda").float() / 3)           # four distinct values
+    cases.append(torch.randn(200001, generator=gen, device="cuda") * 5)                                # far outside [0, 1]
+    cases.append(torch.rand(100004, generator=gen, device="cuda")[3:])                                 # 12-byte offset view
+    for v in cases:
+        n = v.numel()
+        ref = torch.sort(v)[0]
+        for R in (1, 8, 32, 512):
+            ranks = torch.randint(0, n, (R,), generator=gen, device="cuda").cpu().numpy()
+            ranks[0], ranks[-1] = 0, n - 1
+            got = H.order_statistics(v, ranks)
+            want = ref[torch.as_tensor(ranks, device="cuda")]
+            assert torch.equal(got, want), (n, R)
+
+
+def test_gradient_norms_multi_tensor(Q):
+    from quantized_distillation_b200.quantization import help_functions as H
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    ts = [torch.randn(n, generator=gen, device="cuda") * (i + 1) for i, n in enumerate((1, 10, 5000, 16384, 16385, 800000, 75))]
+    got = H.gradient_norms(ts)
+    want = torch.stack([t.double().norm() for t in ts])
+    assert torch.allclose(got.double(), want, rtol=2e-7, atol=0), (got, want)
+    assert torch.equal(got, H.gradient_norms(ts))                 # fixed summation order: reproducible bits
+
+
 def test_error_mapping(Q):
     x = torch.randn(100).cuda()
     with pytest.raises(ValueError):
