@@ -504,6 +504,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the captured training step holds an NCCL all-reduce: no watchdog thread may touch the CUDA API of
+        # this process while a capture is open (the PyTorch CUDA-graphs note asks for the same setting)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     lib = N.lib()
     mode = N.BWD_MINMAX
@@ -551,12 +554,19 @@ def main():
     value = per_gpu_gbs * world
 
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region)
-    hx = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
-    hx.copy_(x)
-    hg = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
-    hg.copy_(g)
-    hq = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
-    hgo = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+    # the pinned buffers are allocated and first touched on the CPUs of this GPU's NUMA node, so that N ranks
+    # on one box do not all stage through the same socket's memory
+    from quantized_distillation_b200 import distributed as D
+    with D.numa_local(local_rank) as numa:
+        hx = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+        hx.copy_(x)
+        hg = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+        hg.copy_(g)
+        hq = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+        hgo = torch.empty(N_ELEMS, dtype=torch.float32).pin_memory()
+        hq.zero_()
+        hgo.zero_()
+        torch.cuda.synchronize(dev)
 
     def e2e_step():
         N.check(lib.qd_uniform_fwd_bwd_host(N.ptr(hx), N.ptr(hg), N.ptr(hq), N.ptr(hgo), N_ELEMS, BUCKET, LEVELS, mode, local_rank))
@@ -587,7 +597,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": round(e2e_gbs, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * N_ELEMS * 4 * world,
                 "d2h_bytes_per_step": 2 * N_ELEMS * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps,
-                "api": "qd_uniform_fwd_bwd_host (pinned host tensors in and out)"},
+                "api": "qd_uniform_fwd_bwd_host (pinned host tensors in and out)", "pinned_buffers_numa": numa.applied},
         "gpu_launches": steps,
         "roofline": {"bound": "hbm", "achieved": round(per_gpu_gbs, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(per_gpu_gbs / peak, 4), "frac_of_nominal_8000": round(per_gpu_gbs / 8000.0, 4),

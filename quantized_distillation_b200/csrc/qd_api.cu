@@ -152,17 +152,9 @@ static int launch_warp(const Params& P, bool vec, cudaStream_t s) {
     const int64_t L = P.geo.row_len;
     if (L <= 256) return vec ? launch_warp_inst<OP, BWD, 2, true>(P, s) : launch_warp_inst<OP, BWD, 2, false>(P, s);
     if (L <= 512) return vec ? launch_warp_inst<OP, BWD, 4, true>(P, s) : launch_warp_inst<OP, BWD, 4, false>(P, s);
-    if constexpr (OP == OP_UNIFORM && BWD == (int)BWD_OFF) {
-        // the plain forward also keeps 2048-element rows in registers (64 floats per lane, one CTA per SM):
-        // the two-pass variant for these rows re-reads from DRAM (see qd_block_path.cuh)
-        if (L > 1024) return launch_warp_inst<OP, BWD, 16, true>(P, s);
-    }
     return vec ? launch_warp_inst<OP, BWD, 8, true>(P, s) : launch_warp_inst<OP, BWD, 8, false>(P, s);
 }
 
-// longest row the register-resident warp path takes for (OP, BWD) when rows are 16-byte aligned
-template <int OP, int BWD>
-static constexpr int64_t warp_path_max_row() { return (OP == OP_UNIFORM && BWD == (int)BWD_OFF) ? 2048 : 1024; }
 
 template <int OP, int BWD, bool STAGED, int GROUP>
 static int launch_block_inst(const Params& P, cudaStream_t s) {
@@ -219,14 +211,16 @@ static int launch_staged_inst(const Params& P, cudaStream_t s) {
     return QD_OK;
 }
 
-// CTA size and ring depth by row length; measured on B200 (tools/block_bench.py, profiles/block_path_r2.md).
+// CTA size and ring depth by row length, from profiles/block_path_r2_variants.md (tools/block_bench.py on B200,
+// every variant forced through the tuning hook): 128 threads up to 3072 floats, 256 up to 12288, 512 up to
+// 24576, 1024 beyond; two rows in flight per CTA up to 4096 floats, the chunk ring alone above.
 // g_tune[1] = longest row with two rows in flight per CTA, g_tune[2] = forced CTA size.
 template <int OP, int BWD>
 static int launch_staged(const Params& P, cudaStream_t s) {
     const int64_t L = P.geo.row_len;
     const int64_t two_max = g_tune[1] >= 0 ? g_tune[1] : kTwoStageMaxRow;
     const bool two = L <= two_max && L <= 24576;
-    int T = L <= 2048 ? 128 : L <= 8192 ? 256 : L <= 24576 ? 512 : 1024;
+    int T = L <= 3072 ? 128 : L <= 12288 ? 256 : L <= 24576 ? 512 : 1024;
     if (g_tune[2] > 0) T = (int)g_tune[2];
     if (two) {
         if (T <= 128) return launch_staged_inst<OP, BWD, 2, 128>(P, s);
@@ -240,11 +234,15 @@ static int launch_staged(const Params& P, cudaStream_t s) {
 
 template <int OP, int BWD>
 static int launch_block(const Params& P, cudaStream_t s) {
-    const int64_t warp2_default = (BWD == (int)BWD_MINMAX) ? kWarpTwoPassMaxRow : 2 * kWarpTwoPassMaxRow;
+    // the warp-per-row two-pass variant only wins for the centroid op on rows below 2048 floats (115 vs 138 us at
+    // 1280); the ops the staged kernel does not implement (stats / scale / stochastic) keep their round-1 thresholds
+    constexpr bool kStagedOp = (OP == OP_UNIFORM || OP == OP_NONUNIFORM);
+    const bool staged_ok = kStagedOp && !P.stochastic;
+    const int64_t warp2_default = !staged_ok ? 2 * kWarpTwoPassMaxRow : (OP == OP_NONUNIFORM ? kWarpTwoPassMaxRow - 1 : 0);
     const int64_t warp2_max = g_tune[0] >= 0 ? g_tune[0] : warp2_default;
     if (P.geo.row_len <= warp2_max) return launch_block_inst<OP, BWD, false, 32>(P, s);               // warp per row, two passes
-    if constexpr (OP == OP_UNIFORM || OP == OP_NONUNIFORM) {
-        if (!P.stochastic) return launch_staged<OP, BWD>(P, s);
+    if constexpr (kStagedOp) {
+        if (staged_ok) return launch_staged<OP, BWD>(P, s);
     }
     return launch_block_inst<OP, BWD, true, kBlockCtaThreads>(P, s);  // scale / stats / stochastic: CTA per row, whole-row staging
 }
@@ -283,8 +281,7 @@ static bool rows_vectorizable(const Params& P) {
 template <int OP, int BWD>
 static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
     if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
-    if (P.geo.row_len <= 1024 || (P.geo.row_len <= warp_path_max_row<OP, BWD>() && rows_vectorizable(P)))
-        return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
+    if (P.geo.row_len <= 1024) return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
     // the CTA / grid paths keep stochastic rounding as a run-time branch of OP_UNIFORM
     constexpr int OP2 = (OP == OP_UNIFORM_STOCH) ? OP_UNIFORM : OP;
     if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP2, BWD>(P, s);
@@ -663,6 +660,15 @@ struct qd_plan {
     std::vector<PlanEntry> host;
     PlanEntry* dev = nullptr;
     float** dev_grads = nullptr;  // count pointers, refreshed per backward call
+    // bucket_size None: every tensor is one row -> the long-row plan (three launches for the whole model)
+    bool long_path = false;
+    std::vector<LongEntry> long_host;
+    LongEntry* long_dev = nullptr;
+    int64_t* long_chunk_starts = nullptr;
+    int64_t* long_row_starts = nullptr;
+    ChunkMinMax* long_partial = nullptr;
+    RowScale* long_rowscale = nullptr;
+    int64_t long_chunks = 0;
     void* workspace = nullptr;    // for tensors that need the grid path
     size_t workspace_bytes = 0;
     int device = 0;
@@ -698,6 +704,34 @@ extern "C" int qd_plan_create(qd_plan** out, int count, const float* const* src,
     }
     p->total_rows = row;
     p->warp_path = p->max_row_len <= 1024;
+    p->long_path = !p->warp_path && bucket == 0;
+    if (p->long_path) {
+        p->long_host.resize(count);
+        std::vector<int64_t> cs(count), rs(count);
+        int64_t chunk = 0;
+        for (int i = 0; i < count; ++i) {
+            const PlanEntry& pe = p->host[i];
+            LongEntry& le = p->long_host[i];
+            le.src = pe.src; le.dst = pe.dst; le.save = nullptr; le.n = pe.n; le.row_len = pe.row_len; le.rows = pe.rows;
+            le.chunks_per_row = (pe.row_len + kPlanChunk - 1) / kPlanChunk;
+            le.chunk_start = chunk; le.row_start = pe.row_start; le.S = pe.S; le.rS = pe.rS; le.lim = pe.lim;
+            cs[i] = chunk; rs[i] = pe.row_start;
+            chunk += le.chunks_per_row * pe.rows;
+        }
+        p->long_chunks = chunk;
+        cudaError_t le_ = cudaMalloc(&p->long_dev, sizeof(LongEntry) * count);
+        if (le_ == cudaSuccess) le_ = cudaMalloc(&p->long_chunk_starts, sizeof(int64_t) * count);
+        if (le_ == cudaSuccess) le_ = cudaMalloc(&p->long_row_starts, sizeof(int64_t) * count);
+        if (le_ == cudaSuccess) le_ = cudaMalloc(&p->long_partial, sizeof(ChunkMinMax) * (size_t)chunk);
+        if (le_ == cudaSuccess) le_ = cudaMalloc(&p->long_rowscale, sizeof(RowScale) * (size_t)row);
+        if (le_ == cudaSuccess) le_ = cudaMemcpy(p->long_dev, p->long_host.data(), sizeof(LongEntry) * count, cudaMemcpyHostToDevice);
+        if (le_ == cudaSuccess) le_ = cudaMemcpy(p->long_chunk_starts, cs.data(), sizeof(int64_t) * count, cudaMemcpyHostToDevice);
+        if (le_ == cudaSuccess) le_ = cudaMemcpy(p->long_row_starts, rs.data(), sizeof(int64_t) * count, cudaMemcpyHostToDevice);
+        if (le_ != cudaSuccess) {
+            qd_plan_destroy(p);
+            return fail(QD_ERR_CUDA, "plan allocation: %s", cudaGetErrorString(le_));
+        }
+    }
     cudaError_t e = cudaMalloc(&p->dev, sizeof(PlanEntry) * count);
     if (e == cudaSuccess) e = cudaMalloc(&p->dev_grads, sizeof(float*) * count);
     if (e == cudaSuccess && !p->warp_path) { e = cudaMalloc(&p->workspace, ws); p->workspace_bytes = ws; }
@@ -715,7 +749,28 @@ extern "C" int qd_plan_destroy(qd_plan* p) {
     if (p->dev) cudaFree(p->dev);
     if (p->dev_grads) cudaFree(p->dev_grads);
     if (p->workspace) cudaFree(p->workspace);
+    if (p->long_dev) cudaFree(p->long_dev);
+    if (p->long_chunk_starts) cudaFree(p->long_chunk_starts);
+    if (p->long_row_starts) cudaFree(p->long_row_starts);
+    if (p->long_partial) cudaFree(p->long_partial);
+    if (p->long_rowscale) cudaFree(p->long_rowscale);
     delete p;
+    return QD_OK;
+}
+
+// three launches for the whole model (qd_plan.cuh, "Long-row plan")
+static int plan_long_forward(const qd_plan* p, int with_save, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    const int64_t cap = (int64_t)di->sms * 4;
+    const int grid = (int)(p->long_chunks < cap ? p->long_chunks : cap);
+    plan_long_stats_partial<<<grid, kPlanChunkThreads, 0, s>>>(p->long_dev, p->count, p->long_chunk_starts, p->long_chunks, p->long_partial);
+    plan_long_stats_final<<<(int)((p->total_rows + 7) / 8), 256, 0, s>>>(p->long_dev, p->count, p->long_row_starts, p->total_rows,
+                                                                        p->long_partial, p->long_rowscale);
+    plan_long_apply<BWD_OFF><<<grid, kPlanChunkThreads, 0, s>>>(p->long_dev, p->count, p->long_chunk_starts, p->long_chunks,
+                                                               p->long_rowscale, with_save, nullptr);
+    QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
 
@@ -724,8 +779,10 @@ extern "C" int qd_plan_set_shadow(qd_plan* p, float* const* shadow) {
     for (int i = 0; i < p->count; ++i) {
         if (shadow[i] == nullptr) return fail(QD_ERR_INVALID_ARG, "shadow[%d] is NULL", i);
         p->host[i].save = shadow[i];
+        if (p->long_path) p->long_host[i].save = shadow[i];
     }
     QD_CUDA(cudaMemcpy(p->dev, p->host.data(), sizeof(PlanEntry) * p->count, cudaMemcpyHostToDevice));
+    if (p->long_path) QD_CUDA(cudaMemcpy(p->long_dev, p->long_host.data(), sizeof(LongEntry) * p->count, cudaMemcpyHostToDevice));
     p->has_shadow = true;
     return QD_OK;
 }
@@ -820,7 +877,8 @@ extern "C" int qd_plan_uniform_fwd(const qd_plan* p, qd_stream_t stream) {
     if (p == nullptr) return fail(QD_ERR_INVALID_ARG, "plan is NULL");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (p->warp_path) return plan_launch<BWD_OFF>(p, nullptr, s);
-    for (int i = 0; i < p->count; ++i) {  // long rows: per-tensor block / grid path
+    if (p->long_path) return plan_long_forward(p, 0, s);
+    for (int i = 0; i < p->count; ++i) {  // buckets of 1025..49152: per-tensor block path
         const PlanEntry& e = p->host[i];
         int rc = qd_uniform_fwd(e.src, e.dst, nullptr, nullptr, nullptr, nullptr, nullptr, e.n, p->bucket, (int)e.S + 1,
                                 nullptr, 0.f, 0, 0, 0, p->workspace, p->workspace_bytes, stream);
@@ -834,7 +892,8 @@ extern "C" int qd_plan_uniform_fwd_save(const qd_plan* p, qd_stream_t stream) {
     if (!p->has_shadow) return fail(QD_ERR_INVALID_ARG, "qd_plan_set_shadow has not been called");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (p->warp_path) return plan_launch<BWD_OFF>(p, nullptr, s, 1);
-    for (int i = 0; i < p->count; ++i) {  // long rows: copy, then the per-tensor block / grid path
+    if (p->long_path) return plan_long_forward(p, 1, s);
+    for (int i = 0; i < p->count; ++i) {  // buckets of 1025..49152: copy, then the per-tensor block path
         const PlanEntry& e = p->host[i];
         QD_CUDA(cudaMemcpyAsync(e.save, e.src, (size_t)e.n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
@@ -845,6 +904,21 @@ extern "C" int qd_plan_uniform_bwd(const qd_plan* p, float* const* grad, int mod
     if (p == nullptr || grad == nullptr) return fail(QD_ERR_INVALID_ARG, "plan or grad is NULL");
     if (mode == QD_BWD_STE) return QD_OK;  // identity
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->long_path) {
+        if (mode == QD_BWD_MINMAX)
+            return fail(QD_ERR_UNSUPPORTED, "minmax backward needs a bucket size (quant_functions.py:332-334)");
+        if (mode != QD_BWD_TRUNCATED) return fail(QD_ERR_INVALID_ARG, "unknown backward mode %d", mode);
+        DevInfo* di;
+        int rc = dev_info(&di);
+        if (rc) return rc;
+        QD_CUDA(cudaMemcpyAsync(p->dev_grads, grad, sizeof(float*) * p->count, cudaMemcpyHostToDevice, s));
+        const int64_t cap = (int64_t)di->sms * 4;
+        const int grid = (int)(p->long_chunks < cap ? p->long_chunks : cap);
+        plan_long_apply<BWD_TRUNC><<<grid, kPlanChunkThreads, 0, s>>>(p->long_dev, p->count, p->long_chunk_starts, p->long_chunks,
+                                                                     p->long_rowscale, 0, p->dev_grads);
+        QD_CUDA(cudaGetLastError());
+        return QD_OK;
+    }
     if (!p->warp_path) {
         for (int i = 0; i < p->count; ++i) {
             const PlanEntry& e = p->host[i];

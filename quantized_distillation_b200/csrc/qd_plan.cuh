@@ -502,3 +502,157 @@ __global__ void __launch_bounds__(kWarpCtaThreads) plan_sgd_step_kernel(const Pl
 }
 
 }  // namespace qd
+
+// =============================================================================================
+// Long-row plan: bucket_size=None (every tensor is ONE row; the post-mortem setting of the drivers,
+// cifar10_test.py:113, 305-317) or rows beyond the warp path.  The per-tensor route costs three launches
+// per tensor (chunk partials, fold, apply); here all tensors share them: THREE launches for the model.
+//   1. every 16 K-element chunk of every tensor -> (min, max)        [one CTA per chunk]
+//   2. one CTA per tensor ROW folds its chunks                        -> alpha, beta
+//   3. element-wise pass over all chunks, in reverse (the tail of the model is still in L2)
+// =============================================================================================
+namespace qd {
+
+constexpr int kPlanChunk = 16384;
+constexpr int kPlanChunkThreads = 512;
+
+struct LongEntry {
+    const float* src;
+    float* dst;
+    float* save;          // optional shadow copy
+    int64_t n;
+    int64_t row_len;      // = n for bucket None, else the bucket
+    int64_t rows;
+    int64_t chunks_per_row;
+    int64_t chunk_start;  // first global chunk
+    int64_t row_start;    // first global row
+    float S, rS, lim;
+};
+
+struct ChunkMinMax { float mn, mx; };
+struct RowScale { float alpha, beta; };
+
+__device__ __forceinline__ int plan_find(const int64_t* starts, int count, int64_t v) {
+    int lo = 0, hi = count - 1;  // largest t with starts[t] <= v
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (starts[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kPlanChunkThreads) plan_long_stats_partial(const LongEntry* __restrict__ entries, int count,
+                                                                            const int64_t* __restrict__ chunk_starts,
+                                                                            int64_t total_chunks, ChunkMinMax* __restrict__ partial) {
+    __shared__ float s_mm[2][kPlanChunkThreads / 32];
+    const uint64_t pol_keep = l2_policy_evict_last();
+    for (int64_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        const LongEntry en = entries[plan_find(chunk_starts, count, c)];
+        const int64_t lc = c - en.chunk_start;
+        const int64_t row = lc / en.chunks_per_row, chunk = lc % en.chunks_per_row;
+        const int64_t row_base = row * en.row_len;
+        const int64_t row_end = min(en.row_len, en.n - row_base);
+        const int64_t off = chunk * kPlanChunk;
+        const int len = (int)min((int64_t)kPlanChunk, row_end - off);
+        const float* src = en.src + row_base + off;
+        float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+        const int vlen = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (len & ~3) : 0;
+        for (int e = threadIdx.x * 4; e < vlen; e += kPlanChunkThreads * 4) {
+            const float4 t = ld_hint4(src + e, pol_keep);
+            mn = min_nan(min_nan(mn, t.x), min_nan(t.y, min_nan(t.z, t.w)));
+            mx = max_nan(max_nan(mx, t.x), max_nan(t.y, max_nan(t.z, t.w)));
+        }
+        for (int e = vlen + threadIdx.x; e < len; e += kPlanChunkThreads) {
+            const float t = src[e];
+            mn = min_nan(mn, t);
+            mx = max_nan(mx, t);
+        }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0) { s_mm[0][threadIdx.x >> 5] = mn; s_mm[1][threadIdx.x >> 5] = mx; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            mn = warp_min(s_mm[0][threadIdx.x & 15]);
+            mx = warp_max(s_mm[1][threadIdx.x & 15]);
+            if (threadIdx.x == 0) { partial[c].mn = mn; partial[c].mx = mx; }
+        }
+        __syncthreads();
+    }
+}
+
+// one warp per global row
+__global__ void __launch_bounds__(256) plan_long_stats_final(const LongEntry* __restrict__ entries, int count,
+                                                             const int64_t* __restrict__ row_starts, int64_t total_rows,
+                                                             const ChunkMinMax* __restrict__ partial, RowScale* __restrict__ rowscale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t grow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (grow >= total_rows) return;
+    const LongEntry en = entries[plan_find(row_starts, count, grow)];
+    const int64_t row = grow - en.row_start;
+    const ChunkMinMax* p = partial + en.chunk_start + row * en.chunks_per_row;
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    for (int64_t c = lane; c < en.chunks_per_row; c += 32) {
+        mn = min_nan(mn, p[c].mn);
+        mx = max_nan(mx, p[c].mx);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+        rowscale[grow].beta = mn;
+        rowscale[grow].alpha = make_alpha(mn, mx);
+    }
+}
+
+// BWD_OFF: dst <- uniformQuantization(src) (+ shadow <- src);  BWD_TRUNC: grad <- (|src| > 1 ? 0 : grad)
+template <int BWD>
+__global__ void __launch_bounds__(kPlanChunkThreads) plan_long_apply(const LongEntry* __restrict__ entries, int count,
+                                                                    const int64_t* __restrict__ chunk_starts, int64_t total_chunks,
+                                                                    const RowScale* __restrict__ rowscale, int with_save,
+                                                                    float* const* __restrict__ grads) {
+    const uint64_t pol_stream = l2_policy_evict_first();
+    for (int64_t it = blockIdx.x; it < total_chunks; it += gridDim.x) {
+        const int64_t c = total_chunks - 1 - it;  // reverse: most recently read data first
+        const int t = plan_find(chunk_starts, count, c);
+        const LongEntry en = entries[t];
+        const int64_t lc = c - en.chunk_start;
+        const int64_t row = lc / en.chunks_per_row, chunk = lc % en.chunks_per_row;
+        const int64_t row_base = row * en.row_len;
+        const int64_t row_end = min(en.row_len, en.n - row_base);
+        const int64_t g0 = row_base + chunk * kPlanChunk;
+        const int len = (int)min((int64_t)kPlanChunk, row_end - chunk * kPlanChunk);
+        if constexpr (BWD == BWD_TRUNC) {
+            float* g = grads[t] + g0;
+            const float* x = en.src + g0;
+            for (int e = threadIdx.x; e < len; e += kPlanChunkThreads) {
+                if (fabsf(x[e]) > 1.0f) g[e] = 0.f;
+            }
+            continue;
+        }
+        const RowScale rsc = rowscale[en.row_start + row];
+        const UniformFast uf = make_uniform_fast(rsc.alpha, en.S);
+        RowState rs;
+        rs.mean = 0.f; rs.alpha = rsc.alpha; rs.beta = rsc.beta;
+        const float* x = en.src + g0;
+        float* q = en.dst + g0;
+        float* sv = (with_save && en.save != nullptr) ? en.save + g0 : nullptr;
+        const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(sv)) & 15) == 0;
+        const int vlen = vec ? (len & ~3) : 0;
+#pragma unroll 2
+        for (int e = threadIdx.x * 4; e < vlen; e += kPlanChunkThreads * 4) {
+            const float4 tv = *reinterpret_cast<const float4*>(x + e);   // L2-resident from pass 1 when the model fits
+            float lv[4];
+            const float4 qo = uniform_quantize_auto4(tv, rs.alpha, rs.beta, uf, en.S, en.rS, en.lim, lv);
+            if (sv != nullptr) st_hint4(sv + e, tv, pol_stream);
+            st_hint4(q + e, qo, pol_stream);
+        }
+        for (int e = vlen + threadIdx.x; e < len; e += kPlanChunkThreads) {
+            const float tv = x[e];
+            float lvl;
+            const float qv = uniform_quantize_auto(tv, rs, uf, en.S, en.rS, en.lim, lvl);
+            if (sv != nullptr) sv[e] = tv;
+            q[e] = qv;
+        }
+    }
+}
+
+}  // namespace qd

@@ -156,6 +156,57 @@ def convert_state_dict_from_data_parallel(state_dict):
     return OrderedDict((k[len("module."):] if k.startswith("module.") else k, v) for k, v in state_dict.items())
 
 
+def gpu_numa_cpus(device_index: int):
+    """(numa node, set of CPU ids) the GPU is attached to, read from sysfs, or None when the platform does
+    not say.  Pinned host buffers that a rank streams to its GPU should be allocated and first touched by a
+    thread running on these CPUs: with 4-8 ranks per box, staging through the other socket's memory halves
+    the host-side bandwidth of every rank."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return node, cpus
+    except Exception:
+        return None
+
+
+class numa_local:
+    """Context manager: pins the calling thread to the CPUs of the GPU's NUMA node (intersected with the
+    CPUs the process may use) for the duration of the block, e.g. while pinned buffers are allocated and
+    first touched; restores the previous affinity on exit.  No-op when sysfs has no answer."""
+
+    def __init__(self, device_index: int):
+        self.info = gpu_numa_cpus(device_index)
+        self.prev = None
+        self.applied = None
+
+    def __enter__(self):
+        try:
+            if self.info is not None:
+                self.prev = os.sched_getaffinity(0)
+                local = self.info[1] & self.prev
+                if local:
+                    os.sched_setaffinity(0, local)
+                    self.applied = {"numa_node": self.info[0], "cpus": len(local)}
+        except Exception:
+            self.applied = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:
+                pass
+        return False
+
+
 def max_over_ranks(value: float, device) -> float:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return value

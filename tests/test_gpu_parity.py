@@ -562,6 +562,34 @@ def test_multi_tensor_plan_matches_per_tensor(Q):
             plan.backward_(grads, "complicated")
             for g, e in zip(grads, expect):
                 assert torch.equal(g, e)
+        # 'truncated' fix-up (also on the long-row plan of bucket None: one launch for all tensors)
+        for p in params:
+            p.mul_(30.0)                                   # some |w| > 1
+        grads = [dev(rng.standard_normal(n).astype(np.float32)) for n in sizes]
+        expect = [torch.where(p.abs() > 1, torch.zeros_like(g), g) for p, g in zip(params, grads)]
+        plan.backward_(grads, "truncated")
+        for g, e in zip(grads, expect):
+            assert torch.equal(g, e)
+        if bucket is None:
+            with pytest.raises(NotImplementedError):
+                plan.backward_(grads, "complicated")
+
+
+def test_long_row_plan_wrn_sized_model_bucket_none(Q):
+    """bucket_size=None on a model with tensors far beyond one SM's shared memory (the post-mortem setting,
+    cifar10_test.py:305-317): three launches for the whole model, bit-identical to the per-tensor op."""
+    from quantized_distillation_b200.plan import QuantizationPlan
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    sizes = [432, 16, 4_460_544, 352, 1_115_136, 10, 123_904, 49_153, 16_384, 16_385, 3]
+    params = [torch.randn(n, generator=gen, device="cuda") * 0.05 for n in sizes]
+    params[2] = params[2].view(352, 352, 6, 6)[:, :, :, :]                     # a 4-D view, like a conv weight
+    for levels in (4, 256):
+        work = [p.clone() for p in params]
+        ref = [Q.uniformQuantization(p, levels, bucket_size=None)[0] for p in work]
+        plan = QuantizationPlan(work, levels=levels, bucket_size=None)
+        master = plan.save_and_quantize_()
+        for w, r, m, o in zip(work, ref, master, params):
+            assert torch.equal(w, r) and torch.equal(m.view(-1), o.reshape(-1))
 
 
 def test_centroid_plan_matches_per_tensor_ops_and_oracle(Q):
