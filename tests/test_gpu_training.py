@@ -206,8 +206,14 @@ def test_whole_step_cuda_graph_matches_eager(env, style):
         assert info["numStepsTrained"] == 8
         finals.append([p.detach().clone() for p in model.parameters()])
     torch.backends.cudnn.deterministic = False
+    # Replay runs the very kernels the eager step launches, so the trajectories can only part where cuDNN
+    # picks another algorithm under capture; after 8 steps at lr 1e-3 that moves a weight by ~1e-7, which
+    # flips its 4-bit level only if it sat on a rounding boundary: at most a handful per tensor.
     for a, b in zip(*finals):
-        assert (a != b).float().mean() < 0.02, "more than a few level flips between graph and eager training"
+        frac = float((a != b).float().mean())
+        step = float((a.max() - a.min()) / 15) if a.numel() > 1 else 1.0
+        assert frac <= 0.002, f"{frac:.5f} of the weights differ between graph and eager training"
+        assert float((a - b).abs().max()) <= 1.01 * step + 1e-6, "a weight moved by more than one quantization level"
 
 
 @pytest.mark.parametrize("graph", [False, True])

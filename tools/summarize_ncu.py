@@ -1,6 +1,10 @@
-"""Turns an ncu report into the tracked summaries under profiles/.
+"""Turns an ncu report (or its `--page raw --csv` export) into the tracked summaries under profiles/.
 
-    python tools/summarize_ncu.py gpurun_out/prof_r1m.ncu-rep profiles/ncu_r1m_kernels.md [profiles/traffic.json]
+    python tools/summarize_ncu.py <report.ncu-rep | raw.csv> profiles/ncu_<tag>.md [profiles/traffic.json]
+
+Per kernel (first capture of each distinct kernel + grid): time, DRAM bytes read / written, DRAM % of peak,
+warp instructions, issue-active %, achieved occupancy, registers, shared memory, and the four largest warp
+stall reasons (stalled warps per issue-active cycle).
 """
 import csv
 import io
@@ -8,45 +12,73 @@ import json
 import subprocess
 import sys
 
-LABELS = {"<2, (int)-1, 2, 1>": "uniform fwd", "<2, 0, 2, 1>": "uniform fwd+bwd STE", "<2, 1, 2, 1>": "uniform fwd+bwd truncated",
-          "<2, 2, 2, 1>": "uniform fwd+bwd min/max (headline)", "<3, 4, 2, 1>": "non-uniform fwd K=4 (register table)",
-          "points_grad_partial": "centroid gradient K=4", "grid_stats_partial": "grid path (bucket None): chunk min/max",
-          "grid_apply": "grid path (bucket None): apply"}
-WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+LABELS = {"warp_rows_kernel<2, (int)-1, 2, 1>": "uniform fwd, bucket 256", "warp_rows_kernel<2, 0, 2, 1>": "uniform fwd+bwd STE, bucket 256",
+          "warp_rows_kernel<2, 1, 2, 1>": "uniform fwd+bwd truncated, bucket 256",
+          "warp_rows_kernel<2, 2, 2, 1>": "uniform fwd+bwd min/max, bucket 256 (HEADLINE)",
+          "warp_rows_kernel<3, 4,": "centroid op K=4 (lane table), bucket 256", "warp_rows_kernel<3, 16,": "centroid op K=16 (lane table), bucket 256",
+          "points_grad_partial": "centroid gradient", "grid_stats_partial": "grid path (bucket None): chunk min/max",
+          "grid_apply": "grid path (bucket None): apply", "staged_rows_kernel<2, (int)-1": "staged path: uniform fwd",
+          "staged_rows_kernel<2, 2": "staged path: fused fwd + min/max bwd", "staged_rows_kernel<3": "staged path: centroid op",
+          "plan_sgd_step_kernel": "fused SGD + fix-up + re-quantize (plan)", "plan_nonuniform_fwd_kernel": "centroid plan forward",
+          "plan_rows_kernel": "uniform plan", "block_rows_kernel": "block path (round-1 kernel)"}
+BASE = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__grid_size"]
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size"]
+
+
+def load(path):
+    if path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    while rows and "Kernel Name" not in rows[0]:
+        rows.pop(0)
+    return rows
 
 
 def main(rep, out_md, traffic_json=None):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
+    rows = load(rep)
     hdr, units = rows[0], rows[1]
-    idx = [hdr.index(w) for w in WANT]
-    mb = lambda v, u: float(v) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1, "Gbyte": 1e3}[u]     # noqa: E731
-    us = lambda v, u: float(v) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(u, 1)                     # noqa: E731
-    seen, lines = set(), []
+    col = {h: i for i, h in enumerate(hdr)}
+    scale_b = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+    scale_t = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    stall_cols = [h for h in hdr if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") and "not_issued" not in h]
+
+    def num(r, name):
+        try:
+            return float(r[col[name]].replace(",", ""))
+        except Exception:
+            return float("nan")
+
+    seen, out = set(), []
     for r in rows[2:]:
-        name = r[idx[0]]
-        if not any(k in name for k in ("warp_rows_kernel", "points_grad", "grid_")) or name in seen:
+        name = r[col["Kernel Name"]]
+        key = (name, r[col["launch__grid_size"]] if "launch__grid_size" in col else "")
+        if key in seen or not any(k in name for k in ("rows_kernel", "points_grad", "grid_", "plan_", "select_")):
             continue
-        seen.add(name)
-        lines.append([r[i] for i in idx])
+        seen.add(key)
+        stalls = sorted(((num(r, c), c.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")) for c in stall_cols), reverse=True)[:4]
+        out.append(dict(
+            name=name, what=next((lab for k, lab in LABELS.items() if k in name), ""),
+            us=num(r, BASE[0]) * scale_t.get(units[col[BASE[0]]], 1.0),
+            rd=num(r, BASE[1]) * scale_b.get(units[col[BASE[1]]], 1e-6), wr=num(r, BASE[2]) * scale_b.get(units[col[BASE[2]]], 1e-6),
+            dram=num(r, BASE[3]), inst=num(r, BASE[4]) / 1e6, issue=num(r, BASE[5]), occ=num(r, BASE[6]),
+            regs=r[col[BASE[7]]], smem=r[col[BASE[8]]] + " " + units[col[BASE[8]]], grid=r[col[BASE[9]]], block=r[col[BASE[10]]],
+            stalls=", ".join(f"{n} {v:.2f}" for v, n in stalls)))
     with open(out_md, "w") as f:
-        f.write("# ncu --set full --clock-control none (tools/profile_ops.py), 64 Mi float32, s=16, bucket 256 unless noted\n\n"
-                "Per launch, first capture of each kernel. Times under ncu are cold-cache and serialised: this table is for DRAM\n"
-                "traffic, instruction counts, occupancy and registers; throughput is timed with CUDA events (bench.py, tools/sweep.py).\n\n"
-                "| kernel | what | us | DRAM read MB | DRAM write MB | DRAM % of peak | warp instr (M) | warps active % | regs | issue active % | grid |\n"
-                "|---|---|---|---|---|---|---|---|---|---|---|\n")
-        for v in lines:
-            what = next((lab for k, lab in LABELS.items() if k in v[0]), "")
-            f.write(f"| `{v[0][:60]}` | {what} | {us(v[1], units[idx[1]]):.1f} | {mb(v[2], units[idx[2]]):.1f} | {mb(v[3], units[idx[3]]):.1f} | "
-                    f"{float(v[4]):.1f} | {float(v[5]) / 1e6:.1f} | {float(v[6]):.1f} | {v[7]} | {float(v[8]):.1f} | {v[9]} |\n")
-            if traffic_json and "<2, 2, 2, 1>" in v[0]:
-                tr = (mb(v[2], units[idx[2]]) + mb(v[3], units[idx[3]])) * 1e6
-                json.dump({"uniform_fwd_bwd_minmax_64Mi_dram_bytes": int(tr), "algorithmic_bytes": 16 * (1 << 26),
-                           "source": f"{out_md}: dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)"},
-                          open(traffic_json, "w"), indent=1)
+        f.write("ncu `--set full --clock-control none`, 64 Mi float32, s=16.  Per launch, first capture of each kernel.  Times under\n"
+                "ncu are cold-cache and serialised: this table is for DRAM traffic, instruction counts, occupancy, registers and stall\n"
+                "reasons; throughput is timed with CUDA events (bench.py, tools/sweep.py, tools/block_bench.py).\n\n"
+                "| kernel | what | us | DRAM rd MB | DRAM wr MB | DRAM % | warp instr M | issue act % | warps act % | regs | dyn smem | grid x block | top stalls (warps per issue-active cycle) |\n"
+                "|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for o in out:
+            f.write(f"| `{o['name'][:70]}` | {o['what']} | {o['us']:.1f} | {o['rd']:.1f} | {o['wr']:.1f} | {o['dram']:.1f} | {o['inst']:.1f} | "
+                    f"{o['issue']:.1f} | {o['occ']:.1f} | {o['regs']} | {o['smem']} | {o['grid']} x {o['block']} | {o['stalls']} |\n")
+            if traffic_json and "warp_rows_kernel<2, 2, 2, 1>" in o["name"]:
+                json.dump({"uniform_fwd_bwd_minmax_64Mi_dram_bytes": int((o["rd"] + o["wr"]) * 1e6), "algorithmic_bytes": 16 * (1 << 26),
+                           "source": f"{out_md} (ncu --set full, one launch of the headline kernel)"}, open(traffic_json, "w"), indent=1)
     print(open(out_md).read())
 
 
