@@ -420,14 +420,9 @@ __device__ __forceinline__ void sgd_step_row(const PlanEntry& en, float* __restr
         rs.alpha2 = make_alpha(qmn, qmx);
         const int imin = first_equal<R, VEC, FULL>(q, qmn, len, lane);
         const int imax = first_equal<R, VEC, FULL>(q, qmx, len, lane);
-        double acc = 0.0;
         const RowDivider div2(rs.alpha2);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (FULL || elem_index<R, VEC>(r, j, lane) < len)
-                    acc += (double)minmax_term(w[4 * r + j], q[4 * r + j], g[4 * r + j], rs.beta2, div2);
+        const double acc = div2.ok ? minmax_lane_sum<R, VEC, FULL, true>(w, q, g, rs.beta2, rs.alpha2, div2, len, lane)
+                                   : minmax_lane_sum<R, VEC, FULL, false>(w, q, g, rs.beta2, rs.alpha2, div2, len, lane);
         const float rb = (float)warp_sum(acc);
         if (imin != imax) {
 #pragma unroll
