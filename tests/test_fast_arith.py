@@ -56,3 +56,75 @@ def test_fast_level_band_is_conservative():
                 accepted = np.abs((t - k).astype(f32)) < lim
                 assert np.array_equal(k[accepted], ref[accepted]), (S, alpha, ulps)
                 assert accepted.mean() > 0.5                # the guard is not vacuous
+
+
+# ---------------------------------------------------------------------------------------------
+# centroid op: one threshold table for both index rules (qd_rowops.cuh, "centroids")
+def _nearest_reference(k, v):
+    """nonUniformQuantization's direct path on one value (quant_functions.py:267-273), float32 arithmetic."""
+    K = len(k)
+    i = int(np.searchsorted(k, v, side="left"))
+    i = min(i, K - 1)
+    if i > 0 and abs(f32(v) - k[i - 1]) < abs(f32(v) - k[i]):
+        i -= 1
+    return i
+
+
+def _key(v):
+    b = int(np.array(v, dtype=f32).view(np.uint32))
+    return (~b) & 0xFFFFFFFF if b & 0x80000000 else b | 0x80000000
+
+
+def _unkey(key):
+    b = (key & 0x7FFFFFFF) if (key & 0x80000000) else (~key) & 0xFFFFFFFF
+    return np.array(b, dtype=np.uint32).view(f32)[()]
+
+
+def _nearest_threshold(k, j):
+    """Host transcription of qd::nearest_threshold: smallest float whose nearest-rule index exceeds j;
+    bisection over the ordered bit patterns, a +-16 ulp window around the float32 midpoint first."""
+    lo, hi = _key(f32(-np.inf)), _key(f32(np.inf))
+    c = f32(k[j] + f32(f32(k[j + 1] - k[j]) * f32(0.5)))
+    ck = _key(c)
+    if lo + 16 < ck < hi - 16:
+        wl, wh = ck - 16, ck + 16
+        if _nearest_reference(k, _unkey(wl)) <= j and _nearest_reference(k, _unkey(wh)) > j:
+            lo, hi = wl + 1, wh
+    while lo < hi:
+        mid = lo + ((hi - lo) >> 1)
+        if _nearest_reference(k, _unkey(mid)) > j:
+            hi = mid
+        else:
+            lo = mid + 1
+    return _unkey(lo)
+
+
+def test_nearest_rule_thresholds():
+    """The nearest-point rule is a monotone step function of x_hat, so K-1 thresholds reproduce it exactly:
+    idx = #{ j : t_j <= x_hat }.  Random, evenly spaced, duplicated and nearly coincident point lists;
+    probes on random values, every threshold +-4 ulp, every point +-3 ulp, zero / negative / > 1 inputs."""
+    rng = np.random.default_rng(0)
+    for trial in range(80):
+        K = int(rng.choice([2, 3, 4, 5, 8, 16, 17]))
+        kind = trial % 4
+        if kind == 0:
+            k = np.sort(rng.random(K).astype(f32))
+        elif kind == 1:
+            k = np.linspace(0, 1, K).astype(f32)
+        elif kind == 2:
+            k = np.sort(rng.random(K).astype(f32))
+            k[K // 2] = k[K // 2 - 1]
+            if K > 3:
+                k[-1] = k[-2]
+        else:
+            k = np.sort((rng.random(K) * 1e-6 + 0.5).astype(f32))
+        t = np.array([_nearest_threshold(k, j) for j in range(K - 1)], dtype=f32)
+        assert np.all(np.diff(t) >= 0)
+        probes = [rng.random(400).astype(f32), np.array([0, 1, -0.0, 1e-30, 2.0, -1.0], dtype=f32)]
+        for v in list(t) + list(k):
+            b = int(np.array([v], dtype=f32).view(np.uint32)[0])
+            probes.append(np.array([max(b + d, 0) for d in range(-4, 5)], dtype=np.uint32).view(f32))
+        xs = np.concatenate(probes)
+        xs = xs[~np.isnan(xs)]
+        for x in xs:
+            assert _nearest_reference(k, x) == int((t <= x).sum()), (k, t, x)
