@@ -88,6 +88,21 @@ int qd_scale_down(const float* x, float* xhat, float* alpha, float* beta, int64_
 int qd_inv_scale_down(const float* y, float* out, const float* alpha, const float* beta, const float* mean,
                       int64_t n, int64_t bucket, qd_stream_t stream);
 
+/* ---- a10: absmax / absnorm scaling -- EXTENSION, parity unpinned ---------
+ * quant_functions.py:109-127, 144-146 cannot execute in the reference (`tensor.max(p=2)`, a bound method stored
+ * as the scale), so no output of the reference exists to compare with.  These entry points implement what the
+ * lines intend once the two slips are repaired: sign = sign(x), v = |x|, norm_b = max v (ABSMAX) or
+ * sqrt(sum v^2) over the padded bucket (ABSNORM), norm_b < 1e-10 -> 1, x_hat = v / norm_b; inverse
+ * y * norm_b * sign (+ mean).  xhat / sign use the padded layout of qd_scale_down; norm: float32[rows]. */
+typedef enum { QD_SCALE_ABSMAX = 1, QD_SCALE_ABSNORM = 2 } qd_abs_scaling;
+int qd_scale_down_abs(const float* x, float* xhat, float* sign, float* norm, int64_t n, int64_t bucket, int kind,
+                      const float* mean, float max_element, qd_stream_t stream);
+int qd_inv_scale_down_abs(const float* y, const float* sign, const float* norm, const float* mean, float* out,
+                          int64_t n, int64_t bucket, qd_stream_t stream);
+/* uniformQuantization(type_of_scaling='absmax'|'absnorm'): q = ((rint(x_hat*S)/S) * norm_b) * sign (+ mean) */
+int qd_uniform_fwd_abs(const float* x, float* q, uint8_t* idx_u8, float* norm, int64_t n, int64_t bucket, int levels,
+                       int kind, const float* mean, float max_element, qd_stream_t stream);
+
 /* ---- a4: uniformQuantization (quant_functions.py:155-194) ----------------
  * q[n] (may alias x: modify_in_place); idx_u8[n] optional integer levels
  * (levels <= 256); levels = s >= 2.  stochastic != 0 selects stochastic

@@ -148,6 +148,40 @@ def uniform_fwd_stochastic(x, s: int, bucket_size, u: np.ndarray):
 
 
 # --------------------------------------------------------------------------
+# a10: absmax / absnorm scaling -- INTENDED semantics, PARITY UNPINNED.
+# quant_functions.py:109-127, 144-146 cannot execute (`tensor.max(p=2)`, `norm_scaling.view` stored as a bound
+# method), so the reference yields no output to pin this against; what follows restates what the lines intend
+# with the two slips repaired, and only checks that the CUDA extension computes exactly that.
+# --------------------------------------------------------------------------
+def abs_scale_down(x, bucket_size, kind, norm=None):
+    """sign, |x| / norm per (padded) bucket; norm = max (absmax) or L2 over the padded bucket (absnorm, float64
+    accumulation rounded once); norm < 1e-10 -> 1.  `norm` overrides the computed scale (for exact checks of what
+    follows it when the float64 sum order differs in the last bit)."""
+    flat = np.asarray(x, dtype=F32).reshape(-1)
+    rows = bucketed(flat, bucket_size)
+    sign = np.sign(rows).astype(F32)
+    v = np.abs(rows)
+    if norm is None:
+        if kind == "absmax":
+            norm = v.max(axis=1)
+        else:
+            norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=1)).astype(F32)
+        norm = np.where(norm < TOL_DIFF_ZERO, F32(1), norm).astype(F32)
+    norm = np.asarray(norm, dtype=F32).reshape(-1)
+    xh = (v / norm[:, None]).astype(F32)
+    return xh, sign, norm, flat.size
+
+
+def uniform_fwd_abs(x, s: int, bucket_size, kind, norm=None):
+    """q = ((rint(x_hat*S)/S) * norm) * sign, one float32 rounding per op (:189-191, :145-146)."""
+    xh, sign, norm, n = abs_scale_down(x, bucket_size, kind, norm)
+    S = F32(s - 1)
+    lvl = np.rint((xh * S).astype(F32)).astype(F32)
+    q = (((lvl / S).astype(F32) * norm[:, None]).astype(F32) * sign).astype(F32)
+    return q.reshape(-1)[:n].reshape(np.shape(x)), lvl.reshape(-1)[:n].astype(np.int64), norm
+
+
+# --------------------------------------------------------------------------
 # a5: backward of uniformQuantization_variable (quant_functions.py:319-406)
 # --------------------------------------------------------------------------
 def uniform_bwd_minmax(x, g, s: int, bucket_size):

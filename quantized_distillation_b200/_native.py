@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libqd_b200.so")
 QD_OK, QD_ERR_INVALID_ARG, QD_ERR_UNSUPPORTED, QD_ERR_CUDA, QD_ERR_WORKSPACE = range(5)
 BWD_STE, BWD_TRUNCATED, BWD_MINMAX = 0, 1, 2
 RULE_NEAREST, RULE_MIDPOINT = 0, 1
+SCALE_ABSMAX, SCALE_ABSNORM = 1, 2
 MAX_STAGED_BUCKET = 49152
 
 _p, _i64, _i32, _u64, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_float, C.c_size_t
@@ -30,6 +31,9 @@ SIGNATURES = {
     "qd_workspace_bytes": (_sz, [_i64, _i64]),
     "qd_scale_down": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _f32, _p, _sz, _p]),
     "qd_inv_scale_down": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "qd_scale_down_abs": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _p, _f32, _p]),
+    "qd_inv_scale_down_abs": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "qd_uniform_fwd_abs": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _f32, _p]),
     "qd_uniform_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _f32, _i32, _u64, _u64, _p, _sz, _p]),
     "qd_uniform_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
     "qd_uniform_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
@@ -112,6 +116,7 @@ def stream_ptr(device=None):
 
 
 _ws = {}
+_WS_MAX_STREAMS = 16
 _WS_FLOOR = 1 << 22          # covers every op whose rows are staged on chip (qd_workspace_bytes <= ~2.5 MB)
 
 
@@ -123,10 +128,12 @@ def workspace(n: int, bucket: int, device) -> torch.Tensor:
         need = max(need, int(lib().qd_workspace_bytes(n, bucket)))
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
-    buf = _ws.get(key)
+    buf = _ws.pop(key, None)
     if buf is None or buf.numel() < need:
         buf = torch.empty(need, dtype=torch.uint8, device=device)
-        _ws[key] = buf
+    _ws[key] = buf                       # re-inserted last: the dict doubles as an LRU list
+    while len(_ws) > _WS_MAX_STREAMS:    # streams come and go (graph capture, user side streams): bound the cache
+        _ws.pop(next(iter(_ws)))
     return buf
 
 

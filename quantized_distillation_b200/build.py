@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("qd_api.cu", "qd_host.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("qd_common.cuh", "qd_rowops.cuh", "qd_warp_path.cuh", "qd_block_path.cuh",
-                                                   "qd_staged_path.cuh", "qd_select.cuh", "qd_grid_path.cuh", "qd_points_grad.cuh", "qd_plan.cuh")]
+                                                   "qd_staged_path.cuh", "qd_abs_path.cuh", "qd_select.cuh", "qd_grid_path.cuh", "qd_points_grad.cuh", "qd_plan.cuh")]
 HEADERS.append(os.path.join(ROOT, "include", "qd_b200.h"))
 OUT = os.path.join(HERE, "libqd_b200.so")
 

@@ -172,10 +172,20 @@ class WeightQuantizer:
         if style not in ("none", "truncated", "complicated"):
             raise ValueError("The specified backprop_quantization_style not recognized")
         self.style = style
-        self.s, scaling = _uniform_levels(quantizationFunctionToUse, numBits)
-        if scaling != "linear":
-            raise NotImplementedError("absmax scaling does not execute in the reference (quant_functions.py:119-126)")
+        self.s, self.scaling = _uniform_levels(quantizationFunctionToUse, numBits)
+        self.bucket_size = bucket_size
         self.params = _selected_parameters(model, quantize_first_and_last_layer)
+        if self.scaling != "linear":
+            # 'uniformAbsMaxScaling' (:206-208) cannot execute in the reference; the intended semantics are an opt-in
+            # extension without a parity target (quantization.quant_functions.ALLOW_UNPINNED_SCALING), per tensor
+            if not quantization.quant_functions.ALLOW_UNPINNED_SCALING:
+                raise NotImplementedError("absmax scaling does not execute in the reference (quant_functions.py:119-126); "
+                                          "set quantization.quant_functions.ALLOW_UNPINNED_SCALING = True for the extension")
+            if style == "complicated":
+                raise ValueError("Linear scaling is necessary to backpropagate")              # quant_functions.py:326-327
+            self.plan = None
+            self._master = [torch.empty_like(p.data) for p in self.params]
+            return
         self.plan = QuantizationPlan(self.params, self.s, bucket_size)
 
     def quantize_weights_model(self, save=True):
@@ -183,16 +193,30 @@ class WeightQuantizer:
         if self.style == "truncated":
             torch._foreach_clamp_min_([p.data for p in self.params], -1.0)   # p.data.clamp_(-1, 1), reference :240-241
             torch._foreach_clamp_max_([p.data for p in self.params], 1.0)
+        if self.plan is None:                                                 # absmax extension: one fused launch per tensor
+            if save:
+                torch._foreach_copy_(self._master, [p.data for p in self.params])
+            for p in self.params:
+                quantization.uniformQuantization(p.data, self.s, type_of_scaling=self.scaling, bucket_size=self.bucket_size,
+                                                 modify_in_place=True)
+            return
         if save:
             self.plan.save_and_quantize_()          # shadow copy + in-place quantization, one launch
         else:
             self.plan.quantize_()
 
     def restore_weights_model(self):
+        if self.plan is None:
+            torch._foreach_copy_([p.data for p in self.params], self._master)
+            return
         self.plan.restore_master()
 
     def backward_quant_weights_model(self):
         if self.style == "none":
+            return
+        if self.plan is None:                                                 # 'truncated' is scaling-agnostic (:263-264)
+            for p in self.params:
+                p.grad.data.masked_fill_(p.data.abs() > 1, 0.0)
             return
         grads = []
         for p in self.params:
@@ -270,7 +294,7 @@ def train_model(model, train_loader, test_loader, initial_learning_rate=0.001, u
 
     fused = bool(fused_optimizer_step and quantizer is not None and device.type == "cuda" and estimate_quant_grad_every == 1
                  and not add_gradient_noise and grad_clipping_threshold is False
-                 and bucket_size is not None and bucket_size <= 512)
+                 and bucket_size is not None and bucket_size <= 512 and quantizer.plan is not None)
     rest_optimizer = None
     if fused:
         chosen = {id(p) for p in quantizer.params}

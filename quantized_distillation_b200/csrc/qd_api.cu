@@ -15,6 +15,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "qd_abs_path.cuh"
 #include "qd_block_path.cuh"
 #include "qd_grid_path.cuh"
 #include "qd_plan.cuh"
@@ -223,6 +224,7 @@ static int launch_staged(const Params& P, cudaStream_t s) {
     int T = L <= 3072 ? 128 : L <= 12288 ? 256 : L <= 24576 ? 512 : 1024;
     if (g_tune[2] > 0) T = (int)g_tune[2];
     if (two) {
+        if (T <= 64) return launch_staged_inst<OP, BWD, 2, 64>(P, s);
         if (T <= 128) return launch_staged_inst<OP, BWD, 2, 128>(P, s);
         if (T <= 256) return launch_staged_inst<OP, BWD, 2, 256>(P, s);
         return launch_staged_inst<OP, BWD, 2, 512>(P, s);
@@ -312,14 +314,26 @@ extern "C" int qd_scale_down(const float* x, float* xhat, float* alpha, float* b
     return run_rows<OP_SCALE, BWD_OFF>(P, workspace, workspace_bytes, s);
 }
 
-__global__ void inv_scale_kernel(const float* __restrict__ y, float* __restrict__ out, const float* __restrict__ alpha,
-                                 const float* __restrict__ beta, const float* __restrict__ mean, Geometry geo) {
+// y*alpha + beta (+ mean): groups of four consecutive elements, one 64-bit division per group when the rows
+// are multiples of four (every bucketed layout of the reference), 128-bit accesses when the pointers allow
+__global__ void __launch_bounds__(256) inv_scale_kernel(const float* __restrict__ y, float* __restrict__ out, const float* __restrict__ alpha,
+                                                        const float* __restrict__ beta, const float* __restrict__ mean, Geometry geo) {
     const float m = mean ? *mean : 0.f;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < geo.n; i += stride) {
-        const int64_t row = i / geo.row_len;
-        float v = from_unit(y[i], alpha[row], beta[row]);  // mul_, add_ (quant_functions.py:142-143)
-        if (mean) v = __fadd_rn(v, m);                      // add_(mean) (:148)
+    const bool vec = (geo.rows == 1 || geo.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t groups = vec ? (geo.n >> 2) : 0;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {
+        const int64_t row = (geo.rows == 1) ? 0 : (gi * 4) / geo.row_len;
+        const float a = alpha[row], b = beta[row];
+        const float4 t = ld_stream4(y + gi * 4);
+        float4 o = make_float4(from_unit(t.x, a, b), from_unit(t.y, a, b), from_unit(t.z, a, b), from_unit(t.w, a, b));  // mul_, add_ (:142-143)
+        if (mean) { o.x = __fadd_rn(o.x, m); o.y = __fadd_rn(o.y, m); o.z = __fadd_rn(o.z, m); o.w = __fadd_rn(o.w, m); }  // add_(mean) (:148)
+        st_stream4(out + gi * 4, o);
+    }
+    for (int64_t i = groups * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < geo.n; i += stride) {
+        const int64_t row = (geo.rows == 1) ? 0 : i / geo.row_len;
+        float v = from_unit(y[i], alpha[row], beta[row]);
+        if (mean) v = __fadd_rn(v, m);
         out[i] = v;
     }
 }
@@ -332,9 +346,72 @@ extern "C" int qd_inv_scale_down(const float* y, float* out, const float* alpha,
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    int64_t need = (n + 255) / 256;
+    int64_t need = (n / 4 + 255) / 256 + 1;
     int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
     inv_scale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, out, alpha, beta, mean, g);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+// ------------------------------------------------------------------ a10 (extension, parity unpinned)
+template <int MODE>
+static int launch_abs(const AbsParams& P, cudaStream_t s) {
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    const int64_t cap = (int64_t)di->sms * 8;
+    if (P.geo.row_len <= 1024) {
+        const int64_t need = (P.geo.rows + 7) / 8;
+        abs_rows_kernel<MODE, 32><<<(int)(need < cap ? need : cap), 256, 0, s>>>(P);
+    } else {
+        abs_rows_kernel<MODE, 256><<<(int)(P.geo.rows < cap ? P.geo.rows : cap), 256, 0, s>>>(P);
+    }
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+static int abs_common(AbsParams& P, const float* x, int64_t n, int64_t bucket, int kind, const float* mean, float max_element) {
+    memset(&P, 0, sizeof(P));
+    if (x == nullptr) return fail(QD_ERR_INVALID_ARG, "x is NULL");
+    if (kind != QD_SCALE_ABSMAX && kind != QD_SCALE_ABSNORM) return fail(QD_ERR_INVALID_ARG, "unknown abs scaling kind %d", kind);
+    if (geometry_of(n, bucket, &P.geo)) return fail(QD_ERR_INVALID_ARG, "bad geometry n=%lld bucket=%lld", (long long)n, (long long)bucket);
+    P.x = x; P.kind = kind; P.mean = mean; P.max_element = max_element;
+    return QD_OK;
+}
+
+extern "C" int qd_scale_down_abs(const float* x, float* xhat, float* sign, float* norm, int64_t n, int64_t bucket, int kind,
+                                 const float* mean, float max_element, qd_stream_t stream) {
+    AbsParams P;
+    int rc = abs_common(P, x, n, bucket, kind, mean, max_element);
+    if (rc) return rc;
+    if (xhat == nullptr || norm == nullptr) return fail(QD_ERR_INVALID_ARG, "xhat and norm are required");
+    P.out = xhat; P.sign = sign; P.norm = norm;
+    return launch_abs<ABS_SCALE>(P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int qd_uniform_fwd_abs(const float* x, float* q, uint8_t* idx_u8, float* norm, int64_t n, int64_t bucket, int levels,
+                                  int kind, const float* mean, float max_element, qd_stream_t stream) {
+    AbsParams P;
+    int rc = abs_common(P, x, n, bucket, kind, mean, max_element);
+    if (rc) return rc;
+    if (q == nullptr) return fail(QD_ERR_INVALID_ARG, "q is NULL");
+    if (levels < 2) return fail(QD_ERR_INVALID_ARG, "levels (s) must be >= 2, got %d", levels);
+    if (idx_u8 != nullptr && levels > 256) return fail(QD_ERR_INVALID_ARG, "idx_u8 needs levels <= 256");
+    P.out = q; P.idx8 = idx_u8; P.norm = norm; P.S = (float)(levels - 1);
+    return launch_abs<ABS_UNIFORM>(P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int qd_inv_scale_down_abs(const float* y, const float* sign, const float* norm, const float* mean, float* out,
+                                     int64_t n, int64_t bucket, qd_stream_t stream) {
+    Geometry g;
+    if (y == nullptr || sign == nullptr || norm == nullptr || out == nullptr) return fail(QD_ERR_INVALID_ARG, "NULL argument");
+    if (geometry_of(n, bucket, &g)) return fail(QD_ERR_INVALID_ARG, "bad geometry");
+    DevInfo* di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    int64_t need = (n + 255) / 256;
+    int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
+    abs_inv_scale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, sign, norm, mean, out, g);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
@@ -475,7 +552,17 @@ __global__ void __launch_bounds__(256) centroid_index_kernel(const float* __rest
     __syncthreads();
     Centroids cen{s_k, s_t, K};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(xhat) | reinterpret_cast<uintptr_t>(unit_out)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(idx8) & 3) == 0;
+    const int64_t groups = vec ? (n >> 2) : 0;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {   // 128-bit loads, four searches in flight
+        const float4 t = ld_stream4(xhat + gi * 4);
+        const int i0 = centroid_index(cen, t.x), i1 = centroid_index(cen, t.y), i2 = centroid_index(cen, t.z), i3 = centroid_index(cen, t.w);
+        if (idx8) *reinterpret_cast<uint32_t*>(idx8 + gi * 4) = (uint32_t)i0 | ((uint32_t)i1 << 8) | ((uint32_t)i2 << 16) | ((uint32_t)i3 << 24);
+        if (idx64) { idx64[gi * 4] = i0; idx64[gi * 4 + 1] = i1; idx64[gi * 4 + 2] = i2; idx64[gi * 4 + 3] = i3; }
+        if (unit_out) st_stream4(unit_out + gi * 4, make_float4(s_k[i0], s_k[i1], s_k[i2], s_k[i3]));
+    }
+    for (int64_t i = groups * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int id = centroid_index(cen, xhat[i]);
         if (idx8) idx8[i] = (uint8_t)id;
         if (idx64) idx64[i] = id;
@@ -491,7 +578,7 @@ extern "C" int qd_centroid_index(const float* xhat, const float* points, int num
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    int64_t need = (n + 255) / 256;
+    int64_t need = (n / 4 + 255) / 256 + 1;
     int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
     centroid_index_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xhat, points, num_points, rule, idx_u8,
                                                                                   idx_i64, unit_out, n);
@@ -593,12 +680,14 @@ __global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __re
         for (int b = 0; b < bits; ++b)
             if (gidx * bits + b < in_bytes) word |= (unsigned long long)packed[gidx * bits + b] << (8 * b);
         const int64_t e0 = gidx * 8;
+        const bool one_row = geo.rows == 1 || geo.row_len % 8 == 0;
+        const int64_t row0 = geo.rows == 1 ? 0 : e0 / geo.row_len;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int64_t e = e0 + j;
             if (e >= geo.n) break;
             const unsigned c = (unsigned)(word >> (j * bits)) & mask;
-            const int64_t row = e / geo.row_len;
+            const int64_t row = one_row ? row0 : e / geo.row_len;   // one 64-bit division per group of eight when rows are multiples of eight
             float unit;
             if (UNIFORM) unit = (S <= 255.0f) ? small_level_to_unit((float)c, S, rS) : level_to_unit((float)c, S);
             else unit = s_pts[c];

@@ -39,7 +39,7 @@ struct StagedScratch {
 // barriers, many rows in flight), rows that fill the shared memory of an SM want one large CTA (all
 // the warps the SM can hold).  Registers are capped at 64 so that 2048 / T CTAs fit.
 template <int OP, int BWD, int STAGES, int T>
-__global__ void __launch_bounds__(T, T == 128 ? 8 : T == 256 ? 4 : T == 512 ? 2 : 1)
+__global__ void __launch_bounds__(T, T == 64 ? 16 : T == 128 ? 8 : T == 256 ? 4 : T == 512 ? 2 : 1)
 staged_rows_kernel(const __grid_constant__ Params P, int stage_floats) {
     static_assert(OP == OP_UNIFORM || OP == OP_NONUNIFORM, "staged path: deterministic uniform / centroid op");
     extern __shared__ __align__(128) float s_dyn[];

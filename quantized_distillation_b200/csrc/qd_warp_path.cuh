@@ -255,8 +255,6 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
             }
         }
 
-        float patch_rb = 0.f;
-        int patch_max = -1, patch_min = 0;
         if constexpr (BWD == BWD_MINMAX) {
             // Second scaling: the reference re-scales q with the same ScalingFunction
             // object, so alpha', beta', argmin', argmax' are those of q
@@ -282,12 +280,18 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
             const double acc = div2.ok ? minmax_lane_sum<R, VEC, FULL, true>(v, qv, gv, rs.beta2, rs.alpha2, div2, len, lane)
                                        : minmax_lane_sum<R, VEC, FULL, false>(v, qv, gv, rs.beta2, rs.alpha2, div2, len, lane);
             const float rb = (float)warp_sum(acc);
-            // +r at argmax', -r at argmin' (the +1/-1 columns of grad_alpha, :380-393).  Only two elements of the
-            // row change: the row is stored as it is and lane 0 patches the two positions afterwards (a compare on
-            // every register of every lane costs four instructions per element)
-            patch_rb = rb;
-            patch_max = (imin != imax) ? imax : -1;
-            patch_min = imin;
+            if (imin != imax) {  // +r at argmax', -r at argmin' (the +1/-1 columns of grad_alpha, :380-393)
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int e = elem_index<R, VEC>(r, j, lane);
+                        if (e == imax) gv[4 * r + j] = __fadd_rn(gv[4 * r + j], rb);
+                        if (e == imin) gv[4 * r + j] = __fadd_rn(gv[4 * r + j], -rb);
+                    }
+            }
+            // (patching the two elements in global memory after the row store instead was measured: the dependent
+            // load-after-store stalls the warp, 177 -> 189 us on the headline workload)
         } else if constexpr (BWD == BWD_TRUNC) {
 #pragma unroll
             for (int i = 0; i < E; ++i) gv[i] = (fabsf(v[i]) > 1.0f) ? 0.f : gv[i];
@@ -302,15 +306,6 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
         }
         if (P.idx8 != nullptr) store_row_u8<R, VEC, FULL>(P.idx8 + base, len, lane, lv);
         if constexpr (BWD != BWD_OFF) store_row<R, VEC, FULL>(P.gout + base, len, lane, gv);
-        if constexpr (BWD == BWD_MINMAX) {
-            __syncwarp();                                      // the row's stores are ordered before the patch
-            if (lane == 0 && patch_max >= 0) {
-                float* pmax = P.gout + base + patch_max;
-                float* pmin = P.gout + base + patch_min;
-                *pmax = __fadd_rn(__ldcg(pmax), patch_rb);
-                *pmin = __fadd_rn(__ldcg(pmin), -patch_rb);
-            }
-        }
         return;
     }
 

@@ -20,6 +20,13 @@ import torch
 
 from .. import _native as N
 
+# Row a10 of the scope table.  'absmax' / 'absnorm' scaling cannot execute in the reference
+# (quant_functions.py:119-126: `tensor.max(p=2)`, a bound method stored as the scale), so there is nothing to be
+# bit-identical TO.  The kernels implement what the lines evidently intend (csrc/qd_abs_path.cuh) as an
+# extension with "parity: unpinned"; it stays refused unless the caller opts in explicitly.
+ALLOW_UNPINNED_SCALING = False
+_ABS_KIND = {"absmax": N.SCALE_ABSMAX, "absnorm": N.SCALE_ABSNORM}
+
 __all__ = ("ScalingFunction", "uniformQuantization", "nonUniformQuantization", "uniformQuantization_variable",
            "nonUniformQuantization_variable", "SearchSorted")
 
@@ -71,11 +78,12 @@ class ScalingFunction(object):
                              "Pass None if you want to avoid using buckets")
         if max_element is True or (max_element is not False and not isinstance(max_element, numbers.Number)):  # :31-33
             raise ValueError("maxElementAllowed must be a number")
-        if type_scaling != "linear":
+        if type_scaling != "linear" and not ALLOW_UNPINNED_SCALING:
             # absmax / absnorm cannot execute in the reference (tensor.max(p=2) is invalid and
             # norm_scaling is bound to a method, quant_functions.py:119-126); no parity target exists.
-            raise NotImplementedError("only 'linear' scaling is implemented: 'absmax'/'absnorm' are broken in the "
-                                      "reference (quant_functions.py:119-126) and used by no experiment")
+            raise NotImplementedError("'absmax'/'absnorm' scaling is broken in the reference (quant_functions.py:119-126) "
+                                      "and used by no experiment; the intended semantics exist here as an extension WITHOUT "
+                                      "a parity target: set quantization.quant_functions.ALLOW_UNPINNED_SCALING = True to use it")
         self.type_scaling = type_scaling
         self.max_element = max_element
         self.subtract_mean = subtract_mean
@@ -122,10 +130,37 @@ class ScalingFunction(object):
             if self._mean_dev is not None:
                 self.mean_tensor = self._mean_dev[0].cpu()
 
+    def _scale_down_abs(self, tensor):
+        """absmax / absnorm (extension, parity unpinned): |x| / norm per bucket, sign kept aside (:109-127)."""
+        self._was_cpu = not tensor.is_cuda
+        self.original_tensor_size = tensor.size()
+        x = _to_device(tensor)
+        n = x.numel()
+        b = _bucket_arg(self.bucket_size)
+        rows, row_len, padded = N.geometry(n, b)
+        self.original_tensor_length = n
+        self.expected_tensor_size = torch.Size((rows, row_len)) if self.bucket_size is not None else torch.Size((n,))
+        self._mean_dev = _mean_tensor(x, self.subtract_mean)
+        self.mean_tensor = self._mean_dev[0] if self._mean_dev is not None else 0
+        out = torch.empty(padded, dtype=torch.float32, device=x.device)
+        sign = torch.empty(padded, dtype=torch.float32, device=x.device)
+        norm = torch.empty((rows, 1) if self.bucket_size is not None else (1,), dtype=torch.float32, device=x.device)
+        N.check(N.lib().qd_scale_down_abs(N.ptr(x), N.ptr(out), N.ptr(sign), N.ptr(norm), n, b, _ABS_KIND[self.type_scaling],
+                                          N.ptr(self._mean_dev), _max_element_arg(self.max_element), N.stream_ptr(x.device)))
+        self.norm_scaling, self.tensor_sign = norm, sign.view(self.expected_tensor_size)
+        out = out.view(self.expected_tensor_size)
+        if self._was_cpu:
+            out, self.norm_scaling, self.tensor_sign = out.cpu(), norm.cpu(), self.tensor_sign.cpu()
+            if self._mean_dev is not None:
+                self.mean_tensor = self._mean_dev[0].cpu()
+        return out
+
     def scale_down(self, tensor):
         """(x - beta)/alpha per bucket; returns the (rows, bucket) tensor, padded
         with copies of the last element like the reference (:56-129)."""
         _check_tensor(tensor)
+        if self.type_scaling != "linear":
+            return self._scale_down_abs(tensor)
         self._was_cpu = not tensor.is_cuda
         self.original_tensor_size = tensor.size()
         x = _to_device(tensor)
@@ -149,6 +184,21 @@ class ScalingFunction(object):
     def inv_scale_down(self, tensor):
         """y*alpha + beta (+ mean), padding dropped, original shape restored (:131-152)."""
         _check_tensor(tensor)
+        if self.type_scaling != "linear":
+            if self.norm_scaling is None or self.tensor_sign is None:
+                raise ValueError("scale_down must be called before inv_scale_down")
+            if tensor.size() != self.expected_tensor_size:
+                raise ValueError("The tensor passed has not the expected size.")
+            was_cpu = not tensor.is_cuda
+            y = _to_device(tensor)
+            n = self.original_tensor_length
+            out = torch.empty(n, dtype=torch.float32, device=y.device)
+            mean_dev = self._mean_dev.to(y.device) if self._mean_dev is not None else None
+            N.check(N.lib().qd_inv_scale_down_abs(N.ptr(y), N.ptr(self.tensor_sign.to(y.device).contiguous()),
+                                                  N.ptr(self.norm_scaling.to(y.device)), N.ptr(mean_dev), N.ptr(out), n,
+                                                  _bucket_arg(self.bucket_size), N.stream_ptr(y.device)))
+            out = out.view(self.original_tensor_size)
+            return out.cpu() if was_cpu else out
         if self.alpha is None:
             raise ValueError("scale_down must be called before inv_scale_down")
         if tensor.size() != self.expected_tensor_size:                                   # :138-139
@@ -180,6 +230,28 @@ def uniformQuantization(tensor, s, type_of_scaling="linear", stochastic_rounding
     x = _to_device(tensor)
     scaling_function._was_cpu = was_cpu
     scaling_function.original_tensor_size = tensor.size()
+    if scaling_function.type_scaling != "linear":        # a10 extension (parity unpinned): one fused kernel as well
+        if stochastic_rounding:
+            raise NotImplementedError("stochastic rounding is not offered with absmax / absnorm scaling")
+        sf = scaling_function
+        n, b = x.numel(), _bucket_arg(bucket_size)
+        rows, row_len, _ = N.geometry(n, b)
+        sf.original_tensor_length = n
+        sf.expected_tensor_size = torch.Size((rows, row_len)) if bucket_size is not None else torch.Size((n,))
+        sf._mean_dev = _mean_tensor(x, subtract_mean)
+        sf.mean_tensor = sf._mean_dev[0] if sf._mean_dev is not None else 0
+        sf.norm_scaling = torch.empty((rows, 1) if bucket_size is not None else (1,), dtype=torch.float32, device=x.device)
+        in_place = modify_in_place and not was_cpu and x.data_ptr() == tensor.data_ptr()
+        q = x if in_place else torch.empty_like(x)
+        N.check(N.lib().qd_uniform_fwd_abs(N.ptr(x), N.ptr(q), None, N.ptr(sf.norm_scaling), n, b, int(s), _ABS_KIND[sf.type_scaling],
+                                           N.ptr(sf._mean_dev), _max_element_arg(max_element), N.stream_ptr(x.device)))
+        q = q.view(tensor.size())
+        if was_cpu:
+            q, sf.norm_scaling = q.cpu(), sf.norm_scaling.cpu()
+            if modify_in_place:
+                tensor.copy_(q)
+                q = tensor
+        return q, sf
     scaling_function._prepare(x)
     in_place = modify_in_place and not was_cpu and x.data_ptr() == tensor.data_ptr()
     q = x if in_place else torch.empty_like(x)

@@ -679,6 +679,52 @@ def test_gradient_norms_multi_tensor(Q):
     assert torch.equal(got, H.gradient_norms(ts))                 # fixed summation order: reproducible bits
 
 
+def test_absmax_absnorm_extension_matches_the_intended_semantics(Q):
+    """Row a10: PARITY UNPINNED -- the reference lines (quant_functions.py:109-127) cannot execute, so this only checks
+    that the opt-in extension computes the intended semantics restated in oracle/quant_oracle.py: refused by default,
+    then scale_down / inv_scale_down / uniformQuantization bit-exact given the per-bucket scale (absmax: exact scale;
+    absnorm: float64 sum rounded once, so the scale itself is compared to one ulp)."""
+    from quantized_distillation_b200.quantization import quant_functions as QF
+    x0 = torch.randn(1000, device="cuda")
+    with pytest.raises(NotImplementedError):
+        Q.uniformQuantization(x0, 8, type_of_scaling="absmax", bucket_size=256)
+    QF.ALLOW_UNPINNED_SCALING = True
+    try:
+        rng = np.random.default_rng(61)
+        for kind in ("absmax", "absnorm"):
+            for bucket in (256, 100, None, 4096):
+                for n in (1, 255, 256, 257, 5000, 70001):
+                    x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+                    if n > 10:
+                        x[3] = 0.0
+                        x[7] = -x[5]
+                    sf = Q.ScalingFunction(kind, False, False, bucket, False)
+                    xh = sf.scale_down(dev(x))
+                    norm_d = sf.norm_scaling.reshape(-1).cpu().numpy()
+                    oxh, osign, onorm, _ = O.abs_scale_down(x, bucket, kind)
+                    if kind == "absmax":
+                        assert_same(norm_d, onorm, f"{kind} norm b={bucket} n={n}")
+                    else:
+                        assert np.all(np.abs(norm_d - onorm) <= np.spacing(onorm)), (kind, bucket, n)
+                        oxh, osign, onorm, _ = O.abs_scale_down(x, bucket, kind, norm=norm_d)
+                    assert_same(xh.cpu().numpy().reshape(oxh.shape), oxh, f"{kind} x_hat b={bucket} n={n}")
+                    assert_same(sf.tensor_sign.cpu().numpy().reshape(osign.shape), osign, f"{kind} sign")
+                    back = sf.inv_scale_down(xh).cpu().numpy().reshape(-1)
+                    want = ((oxh * onorm[:, None]).astype(np.float32) * osign).astype(np.float32).reshape(-1)[:n]
+                    assert_same(back, want, f"{kind} inverse")
+                    for s in (2, 8, 128):
+                        q, sf2 = Q.uniformQuantization(dev(x), s, type_of_scaling=kind, bucket_size=bucket)
+                        nd = sf2.norm_scaling.reshape(-1).cpu().numpy()
+                        oq, _, _ = O.uniform_fwd_abs(x, s, bucket, kind, norm=nd)
+                        assert_same(q.cpu().numpy(), oq, f"{kind} q b={bucket} n={n} s={s}")
+                        lv = np.unique(np.abs(q.cpu().numpy().reshape(-1)[:min(n, bucket or n)]) / max(nd[0], 1e-30) * (s - 1)).round(3)
+                        assert lv.size <= s
+        with pytest.raises(NotImplementedError):
+            Q.uniformQuantization(x0, 8, type_of_scaling="absmax", bucket_size=256, stochastic_rounding=True)
+    finally:
+        QF.ALLOW_UNPINNED_SCALING = False
+
+
 def test_error_mapping(Q):
     x = torch.randn(100).cuda()
     with pytest.raises(ValueError):

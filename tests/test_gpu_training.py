@@ -334,3 +334,30 @@ def test_fused_training_loop_equals_unfused(env, style):
     torch.backends.cudnn.deterministic = False
     same = [float((a == b).float().mean()) for a, b in zip(*finals)]
     assert min(same) == 1.0, same
+
+
+def test_absmax_quantized_training_extension(env):
+    """quantizationFunctionToUse='uniformAbsMaxScaling' (reference :206-208, broken there): refused by default, runs as the
+    opt-in unpinned extension; weights come back with at most 2^(numBits-1) magnitudes per bucket."""
+    Q, cfm, hf = env
+    from quantized_distillation_b200.quantization import quant_functions as QF
+    torch.manual_seed(2)
+    data = hf.synthetic_cifar_loader(3, 25, seed=1)
+    with pytest.raises(NotImplementedError):
+        cfm.train_model_quantized(make_student(cfm), data, data, numBits=3, bucket_size=256, evaluate=False, verbose=False,
+                                  quantizationFunctionToUse="uniformAbsMaxScaling", epochs_to_train=1)
+    QF.ALLOW_UNPINNED_SCALING = True
+    try:
+        model, info = cfm.train_model_quantized(make_student(cfm), data, data, numBits=3, bucket_size=256, evaluate=False,
+                                                verbose=False, quantizationFunctionToUse="uniformAbsMaxScaling", epochs_to_train=1,
+                                                backprop_quantization_style="truncated", print_every=1)
+        assert info["numStepsTrained"] == 3
+        for p in model.parameters():
+            flat = p.detach().abs().view(-1)
+            for start in range(0, flat.numel(), 256):
+                assert torch.unique(flat[start:start + 256]).numel() <= 4          # s = 2^(3-1) magnitudes
+        with pytest.raises(ValueError):
+            cfm.train_model_quantized(make_student(cfm), data, data, numBits=3, bucket_size=256, evaluate=False, verbose=False,
+                                      quantizationFunctionToUse="uniformAbsMaxScaling", backprop_quantization_style="complicated")
+    finally:
+        QF.ALLOW_UNPINNED_SCALING = False

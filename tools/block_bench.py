@@ -51,7 +51,7 @@ def main():
         N.check(lib.qd_debug_set_tuning(key, value))
 
     rows = []
-    buckets = (2048, 8192, 49152) if args.quick else (1280, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152)
+    buckets = (1280, 1536, 2048) if args.quick else (1280, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152)
     for bucket in buckets:
         ws = N.workspace(n, bucket, dev)
         ops = {
@@ -66,10 +66,10 @@ def main():
         variants = {"auto": (-1, -1, -1)}
         if bucket <= 8192:
             variants["warp2"] = (1 << 20, -1, -1)
-        for stages, threads in ((2, 128), (2, 256), (2, 512), (1, 256), (1, 512), (1, 1024)):
+        for stages, threads in ((2, 64), (2, 128), (2, 256), (2, 512), (1, 256), (1, 512), (1, 1024)):
             if stages == 2 and bucket > 24576:
                 continue
-            if threads == 128 and bucket > 4096 or threads == 256 and bucket > 16384 or threads == 1024 and bucket < 8192:
+            if threads == 64 and bucket > 2048 or threads == 128 and bucket > 4096 or threads == 256 and bucket > 16384 or threads == 1024 and bucket < 8192:
                 continue
             if stages == 1 and bucket < 4096:
                 continue

@@ -89,6 +89,18 @@ def run(dev=None, out_path=None, max_log2=28, min_log2=10):
                     N.ptr(gs[i]), N.ptr(idx[i]), None, N.ptr(alpha), 16, N.ptr(gp), n, bucket, N.ptr(ws), ws.numel(), sp))),
             }
             if bucket:
+                # helper entry points (scaling alone, pre-scaled index search, packed codec)
+                xh = [torch.empty(rws * rlen, device=dev) for _ in range(nbuf)]
+                packed = torch.empty((n * 4 + 7) // 8, dtype=torch.uint8, device=dev)
+                ops["scale_down"] = (8, lambda i: N.check(lib.qd_scale_down(
+                    N.ptr(xs[i]), N.ptr(xh[i]), N.ptr(alpha), N.ptr(beta), None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp)))
+                ops["inv_scale_down"] = (8, lambda i: N.check(lib.qd_inv_scale_down(
+                    N.ptr(xh[i]), N.ptr(qs[i]), N.ptr(alpha), N.ptr(beta), None, n, bucket, sp)))
+                ops["centroid_index_K4_u8"] = (5, lambda i: N.check(lib.qd_centroid_index(
+                    N.ptr(xh[i]), N.ptr(pts4), 4, N.RULE_MIDPOINT, N.ptr(idx[i]), None, None, n, sp)))
+                ops["pack_4bit"] = (1.5, lambda i: N.check(lib.qd_pack_indices(N.ptr(idx[i]), N.ptr(packed), n, 4, sp)))
+                ops["unpack_dequant_uniform_4bit"] = (4.5, lambda i: N.check(lib.qd_unpack_dequant_uniform(
+                    N.ptr(packed), 4, N.ptr(alpha), N.ptr(beta), N.ptr(qs[i]), n, bucket, 16, sp)))
                 ops["uniform_fwd_bwd_minmax"] = (16, lambda i: N.check(lib.qd_uniform_fwd_bwd(
                     N.ptr(xs[i]), N.ptr(gs[i]), N.ptr(qs[i]), N.ptr(gos[i]), n, bucket, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(), sp)))
                 ops["uniform_bwd_minmax"] = (12, lambda i: N.check(lib.qd_uniform_bwd(
