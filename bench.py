@@ -279,7 +279,7 @@ def leg_settings(kind, world):
                         quantize_first_and_last_layer=False))
 
 
-def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False, flat=True):
+def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False, flat=True, fused=False):
     """CIFAR10-shaped quantized distillation steps/s (BASELINE configs 2-4), synthetic data,
     random-init weights.  Every step copies its batch from pinned host memory and reads the
     loss back (print_every=1), so the number is end to end.  world > 1: FlatDataParallel (one
@@ -315,7 +315,8 @@ def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False, flat=True)
         model = D.wrap_data_parallel(student, dev, flat=flat)
         info = cfm.train_model_quantized(model, data, data, numBits=bits, bucket_size=256, use_distillation_loss=True,
                                          teacher_model=teacher, epochs_to_train=1, print_every=1, verbose=False, evaluate=False,
-                                         max_steps=total, step_hook=hook, cuda_graph_step=graph, **st["kw"])[1]
+                                         max_steps=total, step_hook=hook, cuda_graph_step=graph, fused_optimizer_step=fused,
+                                         **st["kw"])[1]
         label = f"{bits}-bit quantized distillation, bucket 256 (BASELINE config {2 if kind == 'student' else 3})"
     torch.cuda.synchronize(dev)
     ms = ev["t0"].elapsed_time(ev["t1"]) / steps
@@ -326,6 +327,8 @@ def run_train_leg(kind, world, rank, dev, steps, warmup, graph=False, flat=True)
                      "synthetic CIFAR-shaped data, batch copied from pinned host memory and loss read back every step",
            "steps_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 3), "images_per_s": round(per_gpu_batch * world * 1e3 / ms, 1),
            "steps": steps, "warmup": warmup, "n_gpus": world, "cuda_graph_step": bool(graph)}
+    if fused:
+        out["fused_optimizer_step"] = bool(info.get("fused_optimizer_step", False))
     if graph:
         out["captured"] = bool(info.get("cuda_graph_step", False))
     del student, teacher
@@ -432,7 +435,12 @@ def train_legs(which, world, rank, dev, steps, with_cpu):
         wsteps = steps if kind != "wrn" else max(10, steps // 2)
         leg = {"eager": run_train_leg(kind, world, rank, dev, wsteps, 8, graph=False)}
         leg["cuda_graph_step"] = run_train_leg(kind, world, rank, dev, wsteps, 8, graph=True)
-        best = max((leg["eager"], leg["cuda_graph_step"]), key=lambda r: r["steps_per_s"])
+        cands = [leg["eager"], leg["cuda_graph_step"]]
+        if kind != "diffquant":
+            # restore + gradient fix-up + SGD + next step's quantization as one kernel (qd_plan_sgd_step), inside the graph
+            leg["cuda_graph_fused_optimizer"] = run_train_leg(kind, world, rank, dev, wsteps, 8, graph=True, fused=True)
+            cands.append(leg["cuda_graph_fused_optimizer"])
+        best = max(cands, key=lambda r: r["steps_per_s"])
         leg["steps_per_s"], leg["images_per_s"], leg["ms_per_step"] = best["steps_per_s"], best["images_per_s"], best["ms_per_step"]
         if world == 1 and rank == 0:
             leg["reference_style_gpu"] = reference_style_leg(kind, dev, max(6, wsteps // 2), 3)

@@ -322,13 +322,21 @@ __global__ void __launch_bounds__(256) inv_scale_kernel(const float* __restrict_
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const bool vec = (geo.rows == 1 || geo.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     const int64_t groups = vec ? (geo.n >> 2) : 0;
-    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {
-        const int64_t row = (geo.rows == 1) ? 0 : (gi * 4) / geo.row_len;
+    // the row of a group advances by a fixed (rows, remainder) step per iteration: two divisions per THREAD, none per group
+    const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t row = (geo.rows == 1) ? 0 : (g0 * 4) / geo.row_len;
+    int64_t rem = (geo.rows == 1) ? 0 : (g0 * 4) - row * geo.row_len;
+    const int64_t step_rows = (geo.rows == 1) ? 0 : (stride * 4) / geo.row_len;
+    const int64_t step_rem = (geo.rows == 1) ? 0 : (stride * 4) - step_rows * geo.row_len;
+    for (int64_t gi = g0; gi < groups; gi += stride) {
         const float a = alpha[row], b = beta[row];
         const float4 t = ld_stream4(y + gi * 4);
         float4 o = make_float4(from_unit(t.x, a, b), from_unit(t.y, a, b), from_unit(t.z, a, b), from_unit(t.w, a, b));  // mul_, add_ (:142-143)
         if (mean) { o.x = __fadd_rn(o.x, m); o.y = __fadd_rn(o.y, m); o.z = __fadd_rn(o.z, m); o.w = __fadd_rn(o.w, m); }  // add_(mean) (:148)
         st_stream4(out + gi * 4, o);
+        row += step_rows;
+        rem += step_rem;
+        if (rem >= geo.row_len) { rem -= geo.row_len; ++row; }
     }
     for (int64_t i = groups * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < geo.n; i += stride) {
         const int64_t row = (geo.rows == 1) ? 0 : i / geo.row_len;
@@ -542,7 +550,43 @@ extern "C" int qd_nonuniform_bwd(const float* g, const uint8_t* idx_u8, const in
     return QD_OK;
 }
 
-// index search on pre-scaled values (pre-processed path of the reference)
+// index search on pre-scaled values (pre-processed path of the reference): 128-bit loads, lane-table search for
+// K <= 32 (the loop runs the same number of times in every thread of a warp, so the shuffles are warp-uniform)
+template <int KP>
+__device__ __forceinline__ void centroid_index_body(const Centroids& cen, const float* s_k, const float* __restrict__ xhat, uint8_t* idx8,
+                                                    int64_t* idx64, float* unit_out, int64_t n) {
+    constexpr bool LANES = KP <= 32;
+    LaneSearch<LANES ? KP : 1> ls;
+    if constexpr (LANES) ls.load(cen, threadIdx.x & 31);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(xhat) | reinterpret_cast<uintptr_t>(unit_out)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(idx8) & 3) == 0;
+    const int64_t groups = vec ? (n >> 2) : 0;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < groups; base += stride) {
+        const int64_t gi = base + threadIdx.x;
+        const bool act = gi < groups;
+        const float4 t = act ? ld_stream4(xhat + gi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float xv[4] = {t.x, t.y, t.z, t.w};
+        int id[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if constexpr (LANES) id[j] = ls.index(xv[j]);
+            else id[j] = padded_count<KP>(cen.t, xv[j]);
+        }
+        if (act) {
+            if (idx8) *reinterpret_cast<uint32_t*>(idx8 + gi * 4) = (uint32_t)id[0] | ((uint32_t)id[1] << 8) | ((uint32_t)id[2] << 16) | ((uint32_t)id[3] << 24);
+            if (idx64) { idx64[gi * 4] = id[0]; idx64[gi * 4 + 1] = id[1]; idx64[gi * 4 + 2] = id[2]; idx64[gi * 4 + 3] = id[3]; }
+            if (unit_out) st_stream4(unit_out + gi * 4, make_float4(s_k[id[0]], s_k[id[1]], s_k[id[2]], s_k[id[3]]));
+        }
+    }
+    for (int64_t i = groups * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int id = centroid_index(cen, xhat[i]);
+        if (idx8) idx8[i] = (uint8_t)id;
+        if (idx64) idx64[i] = id;
+        if (unit_out) unit_out[i] = s_k[id];
+    }
+}
+
 __global__ void __launch_bounds__(256) centroid_index_kernel(const float* __restrict__ xhat, const float* __restrict__ points,
                                                             int K, int rule, uint8_t* idx8, int64_t* idx64,
                                                             float* unit_out, int64_t n) {
@@ -551,23 +595,11 @@ __global__ void __launch_bounds__(256) centroid_index_kernel(const float* __rest
     centroid_setup(s_k, s_t, points, K, rule);
     __syncthreads();
     Centroids cen{s_k, s_t, K};
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const bool vec = ((reinterpret_cast<uintptr_t>(xhat) | reinterpret_cast<uintptr_t>(unit_out)) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(idx8) & 3) == 0;
-    const int64_t groups = vec ? (n >> 2) : 0;
-    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {   // 128-bit loads, four searches in flight
-        const float4 t = ld_stream4(xhat + gi * 4);
-        const int i0 = centroid_index(cen, t.x), i1 = centroid_index(cen, t.y), i2 = centroid_index(cen, t.z), i3 = centroid_index(cen, t.w);
-        if (idx8) *reinterpret_cast<uint32_t*>(idx8 + gi * 4) = (uint32_t)i0 | ((uint32_t)i1 << 8) | ((uint32_t)i2 << 16) | ((uint32_t)i3 << 24);
-        if (idx64) { idx64[gi * 4] = i0; idx64[gi * 4 + 1] = i1; idx64[gi * 4 + 2] = i2; idx64[gi * 4 + 3] = i3; }
-        if (unit_out) st_stream4(unit_out + gi * 4, make_float4(s_k[i0], s_k[i1], s_k[i2], s_k[i3]));
-    }
-    for (int64_t i = groups * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int id = centroid_index(cen, xhat[i]);
-        if (idx8) idx8[i] = (uint8_t)id;
-        if (idx64) idx64[i] = id;
-        if (unit_out) unit_out[i] = s_k[id];
-    }
+    if (K <= 4) centroid_index_body<4>(cen, s_k, xhat, idx8, idx64, unit_out, n);
+    else if (K <= 8) centroid_index_body<8>(cen, s_k, xhat, idx8, idx64, unit_out, n);
+    else if (K <= 16) centroid_index_body<16>(cen, s_k, xhat, idx8, idx64, unit_out, n);
+    else if (K <= 32) centroid_index_body<32>(cen, s_k, xhat, idx8, idx64, unit_out, n);
+    else centroid_index_body<256>(cen, s_k, xhat, idx8, idx64, unit_out, n);
 }
 
 extern "C" int qd_centroid_index(const float* xhat, const float* points, int num_points, int rule, uint8_t* idx_u8,
@@ -628,23 +660,37 @@ extern "C" int qd_index_histogram(const uint8_t* idx_u8, int64_t n, int num_bins
 }
 
 // ------------------------------------------------------------------ f2: packed codec
-// one thread = 8 consecutive codes in, `bits` bytes out
+// one thread = 8 consecutive codes in (one 64-bit load), `bits` bytes out (one store of that width)
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ idx, uint8_t* __restrict__ packed, int64_t n,
                                                   int bits) {
     const int64_t groups = (n + 7) / 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const unsigned mask = (1u << bits) - 1u;
+    const int64_t out_bytes = (n * bits + 7) / 8;
+    const bool in_vec = (reinterpret_cast<uintptr_t>(idx) & 7) == 0;
+    const bool out_vec = (reinterpret_cast<uintptr_t>(packed) & 7) == 0;
     for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += stride) {
-        unsigned long long word = 0;
         const int64_t e0 = gidx * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned c = (e0 + j < n) ? (idx[e0 + j] & mask) : 0u;
-            word |= (unsigned long long)c << (j * bits);
+        unsigned long long codes = 0;
+        if (in_vec && e0 + 8 <= n) {
+            codes = *reinterpret_cast<const unsigned long long*>(idx + e0);
+        } else {
+            for (int j = 0; j < 8; ++j)
+                if (e0 + j < n) codes |= (unsigned long long)idx[e0 + j] << (8 * j);
         }
-        const int64_t out_bytes = (n * bits + 7) / 8;
-        for (int b = 0; b < bits; ++b)
-            if (gidx * bits + b < out_bytes) packed[gidx * bits + b] = (uint8_t)(word >> (8 * b));
+        unsigned long long word = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) word |= (unsigned long long)((unsigned)(codes >> (8 * j)) & mask) << (j * bits);
+        uint8_t* dst = packed + gidx * bits;
+        if (out_vec && (gidx + 1) * bits <= out_bytes) {
+            if (bits == 8) *reinterpret_cast<unsigned long long*>(dst) = word;
+            else if (bits == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)word;
+            else if (bits == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word;
+            else *dst = (uint8_t)word;
+        } else {
+            for (int b = 0; b < bits; ++b)
+                if (gidx * bits + b < out_bytes) dst[b] = (uint8_t)(word >> (8 * b));
+        }
     }
 }
 
@@ -661,6 +707,9 @@ extern "C" int qd_pack_indices(const uint8_t* idx_u8, uint8_t* packed, int64_t n
     return QD_OK;
 }
 
+// one thread = FOUR consecutive elements: their codes sit in at most four bytes starting at byte 4*g*bits/8, the
+// four dequantized values leave as one 128-bit store (a warp writes 512 contiguous bytes); the row of a group
+// advances by a fixed step per iteration (no division per element)
 template <bool UNIFORM>
 __global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __restrict__ packed, int bits,
                                                             const float* __restrict__ points, int K,
@@ -671,28 +720,44 @@ __global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __re
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pts[i] = (i < K) ? points[i] : 0.f;
         __syncthreads();
     }
-    const int64_t groups = (geo.n + 7) / 8;
+    const int64_t groups = (geo.n + 3) / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const unsigned mask = (1u << bits) - 1u;
     const int64_t in_bytes = (geo.n * bits + 7) / 8;
-    for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += stride) {
-        unsigned long long word = 0;
-        for (int b = 0; b < bits; ++b)
-            if (gidx * bits + b < in_bytes) word |= (unsigned long long)packed[gidx * bits + b] << (8 * b);
-        const int64_t e0 = gidx * 8;
-        const bool one_row = geo.rows == 1 || geo.row_len % 8 == 0;
-        const int64_t row0 = geo.rows == 1 ? 0 : e0 / geo.row_len;
+    const bool ovec = (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+    const bool same_row = geo.rows == 1 || geo.row_len % 4 == 0;   // the four elements of a group share their row
+    const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t row = (geo.rows == 1) ? 0 : (g0 * 4) / geo.row_len;
+    int64_t rem = (geo.rows == 1) ? 0 : (g0 * 4) - row * geo.row_len;
+    const int64_t step_rows = (geo.rows == 1) ? 0 : (stride * 4) / geo.row_len;
+    const int64_t step_rem = (geo.rows == 1) ? 0 : (stride * 4) - step_rows * geo.row_len;
+    for (int64_t gidx = g0; gidx < groups; gidx += stride) {
+        const int64_t e0 = gidx * 4;
+        const int64_t bit0 = e0 * bits;
+        const int64_t b0 = bit0 >> 3;
+        uint32_t word = 0;
+        const int nbytes = (4 * bits + (int)(bit0 & 7) + 7) >> 3;   // 1 (bits 1, 2), 2 (bits 4) or 4 (bits 8)
+        for (int b = 0; b < nbytes; ++b)
+            if (b0 + b < in_bytes) word |= (uint32_t)packed[b0 + b] << (8 * b);
+        word >>= (unsigned)(bit0 & 7);
+        float o[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t e = e0 + j;
-            if (e >= geo.n) break;
-            const unsigned c = (unsigned)(word >> (j * bits)) & mask;
-            const int64_t row = one_row ? row0 : e / geo.row_len;   // one 64-bit division per group of eight when rows are multiples of eight
-            float unit;
-            if (UNIFORM) unit = (S <= 255.0f) ? small_level_to_unit((float)c, S, rS) : level_to_unit((float)c, S);
-            else unit = s_pts[c];
-            q[e] = from_unit(unit, alpha[row], beta[row]);
+        for (int j = 0; j < 4; ++j) {
+            const unsigned c = (word >> (j * bits)) & mask;
+            int64_t r = row;
+            if (!same_row) r = (e0 + j) / geo.row_len;
+            const float unit = UNIFORM ? ((S <= 255.0f) ? small_level_to_unit((float)c, S, rS) : level_to_unit((float)c, S)) : s_pts[c];
+            o[j] = (e0 + j < geo.n) ? from_unit(unit, alpha[r], beta[r]) : 0.f;
         }
+        if (ovec && e0 + 4 <= geo.n) {
+            st_stream4(q + e0, make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+            for (int j = 0; j < 4; ++j)
+                if (e0 + j < geo.n) q[e0 + j] = o[j];
+        }
+        row += step_rows;
+        rem += step_rem;
+        if (rem >= geo.row_len) { rem -= geo.row_len; ++row; }
     }
 }
 
@@ -704,7 +769,7 @@ static int unpack_common(const uint8_t* packed, int bits, const float* alpha, co
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    int64_t need = ((n + 7) / 8 + 255) / 256;
+    int64_t need = ((n + 3) / 4 + 255) / 256;
     *grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
     return QD_OK;
 }
