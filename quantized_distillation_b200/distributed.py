@@ -61,16 +61,23 @@ def wrap_ddp(model, device):
 
 
 class FlatDataParallel(torch.nn.Module):
-    """Replicated module whose gradients live in one flat buffer reduced by one collective.
+    """Replicated module whose gradients live in one flat buffer reduced by one collective per BUCKET.
 
     ``p.grad`` of every trainable parameter is a view of ``flat_grad`` (each tensor starts on a
     256-byte boundary, so the plan's 128-bit gradient fix-up kernels apply).  Autograd accumulates
-    in place into an existing ``.grad``, ``zero_grad`` is one memset, ``reduce_gradients`` one
-    all-reduce (AVG on NCCL; SUM then scale on gloo).  Parameters and buffers are broadcast from
-    rank 0 once at construction; batch-norm statistics stay replica-local afterwards (the
-    reference's ``nn.DataParallel`` keeps only replica 0's, cifar10_wideResNet.py:68-69)."""
+    in place into an existing ``.grad``, ``zero_grad`` is one memset.  The buffer is cut into
+    contiguous buckets of about ``bucket_mb`` (one bucket when the model is smaller: the 4 MB
+    student).  With several buckets, each bucket's all-reduce (AVG on NCCL; SUM then scale on gloo)
+    is issued on a communication stream as soon as the last gradient of the bucket has been
+    accumulated (post-accumulate-grad hooks), so it overlaps the rest of the backward pass;
+    ``reduce_gradients()`` issues whatever is still pending and joins the stream.  All of it is
+    stream-ordered device work, so the whole training step -- collectives included -- can still be
+    captured in ONE CUDA graph (the side stream forks from and joins the capturing stream).
+    Parameters and buffers are broadcast from rank 0 once at construction; batch-norm statistics
+    stay replica-local afterwards (the reference's ``nn.DataParallel`` keeps only replica 0's,
+    cifar10_wideResNet.py:68-69)."""
 
-    def __init__(self, module, process_group=None):
+    def __init__(self, module, process_group=None, bucket_mb=32.0):
         super().__init__()
         self.module = module
         self.process_group = process_group
@@ -85,14 +92,59 @@ class FlatDataParallel(torch.nn.Module):
         device, dtype = params[0].device, params[0].dtype
         pad = lambda n: -(-n // 64) * 64                                  # 256-byte granules
         self.flat_grad = torch.zeros(sum(pad(p.numel()) for p in params), dtype=dtype, device=device)
-        off = 0
+        off, spans = 0, []
         for p in params:
             if p.device != device or p.dtype != dtype or not p.is_contiguous():
                 raise ValueError("FlatDataParallel needs contiguous parameters of one dtype on one device")
             p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+            spans.append((off, off + pad(p.numel())))
             off += pad(p.numel())
         self._params = params
         self._nccl = self.world > 1 and dist.get_backend(process_group) == "nccl"
+        # buckets: contiguous runs of parameters, in registration order, of >= bucket_mb each
+        limit = int(bucket_mb * (1 << 20) / self.flat_grad.element_size())
+        self._buckets, start, members = [], 0, []
+        for i, (lo, hi) in enumerate(spans):
+            members.append(i)
+            if hi - start >= limit or i == len(spans) - 1:
+                self._buckets.append({"lo": start, "hi": hi, "members": members, "pending": len(members), "sent": False})
+                start, members = hi, []
+        self._bucket_of = {}
+        for b, bucket in enumerate(self._buckets):
+            for i in bucket["members"]:
+                self._bucket_of[i] = b
+        # several buckets: each one is reduced from the backward pass as soon as it is complete (on a side stream on CUDA)
+        self._early = self.world > 1 and len(self._buckets) > 1
+        self._comm_stream = torch.cuda.Stream(device) if (self._early and device.type == "cuda") else None
+        if self._early:
+            for i, p in enumerate(params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    # ---- bucketed, overlapped reduction ---------------------------------------------------------
+    def _make_hook(self, index):
+        def hook(_param):
+            bucket = self._buckets[self._bucket_of[index]]
+            bucket["pending"] -= 1
+            if bucket["pending"] == 0 and not bucket["sent"]:
+                self._send(bucket)
+        return hook
+
+    def _all_reduce(self, view):
+        if self._nccl:
+            dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.process_group)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.process_group)
+            view.mul_(1.0 / self.world)
+
+    def _send(self, bucket):
+        bucket["sent"] = True
+        view = self.flat_grad[bucket["lo"]:bucket["hi"]]
+        if self._comm_stream is None:
+            self._all_reduce(view)
+            return
+        self._comm_stream.wait_stream(torch.cuda.current_stream(self.flat_grad.device))   # the bucket's gradients are complete
+        with torch.cuda.stream(self._comm_stream):
+            self._all_reduce(view)
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
@@ -101,6 +153,8 @@ class FlatDataParallel(torch.nn.Module):
         """One memset; the views stay bound whatever ``set_to_none`` says (a ``None`` gradient
         would make autograd allocate a fresh tensor outside the flat buffer)."""
         self.flat_grad.zero_()
+        for bucket in self._buckets:
+            bucket["pending"], bucket["sent"] = len(bucket["members"]), False
 
     def views_intact(self) -> bool:
         """True while every ``p.grad`` still aliases the flat buffer (an optimizer's
@@ -110,23 +164,25 @@ class FlatDataParallel(torch.nn.Module):
         return all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self._params)
 
     def reduce_gradients(self):
-        """Average of the flat gradient over the replicas: ONE collective per step."""
+        """Average of the flat gradient over the replicas.  Buckets whose all-reduce was already issued from
+        the backward pass are only waited for; the others (single-bucket models, parameters that took no
+        part in the backward pass) are reduced now."""
         if self.world == 1:
             return
-        if self._nccl:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.process_group)
-        else:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
-            self.flat_grad.mul_(1.0 / self.world)
+        for bucket in self._buckets:
+            if not bucket["sent"]:
+                self._send(bucket)
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.flat_grad.device).wait_stream(self._comm_stream)
 
 
-def wrap_data_parallel(model, device=None, flat=True):
+def wrap_data_parallel(model, device=None, flat=True, bucket_mb=32.0):
     """Data-parallel wrapper of the training harness: :class:`FlatDataParallel` (graph-capturable,
-    one all-reduce) or stock DDP (``flat=False``).  Single process: the model itself."""
+    one all-reduce per ``bucket_mb`` of gradients) or stock DDP (``flat=False``).  Single process: the model itself."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return model
     if flat:
-        return FlatDataParallel(model)
+        return FlatDataParallel(model, bucket_mb=bucket_mb)
     return wrap_ddp(model, device if device is not None else next(model.parameters()).device)
 
 

@@ -136,8 +136,12 @@ def _flat_worker(rank, world, port, ret):
     from quantized_distillation_b200 import distributed as D
     w, r, device = D.init_distributed(backend="gloo")
     torch.manual_seed(1234 + r)                                    # DIFFERENT init per rank: the wrapper must broadcast rank 0's
-    model = D.wrap_data_parallel(_student_no_bn(), device)
+    # 0.25 MB buckets: the 4 MB gradient buffer is cut into several, each reduced from a post-accumulate-grad hook
+    model = D.wrap_data_parallel(_student_no_bn(), device, bucket_mb=0.25)
     assert isinstance(model, D.FlatDataParallel) and model.views_intact()
+    assert len(model._buckets) > 3 and model._early
+    assert model._buckets[0]["lo"] == 0 and model._buckets[-1]["hi"] == model.flat_grad.numel()
+    assert all(a["hi"] == b["lo"] for a, b in zip(model._buckets, model._buckets[1:]))
     lo = model.flat_grad.data_ptr()
     assert all((p.grad.data_ptr() - lo) % 256 == 0 for p in model.parameters())   # 128-bit kernels need aligned rows
     global_batches = hf.synthetic_cifar_loader(3, 8, seed=7, pin=False)
