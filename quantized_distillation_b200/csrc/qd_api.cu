@@ -213,15 +213,16 @@ static int launch_staged_inst(const Params& P, cudaStream_t s) {
 }
 
 // CTA size and ring depth by row length, from profiles/block_path_r2_variants.md (tools/block_bench.py on B200,
-// every variant forced through the tuning hook): 128 threads up to 3072 floats, 256 up to 12288, 512 up to
-// 24576, 1024 beyond; two rows in flight per CTA up to 4096 floats, the chunk ring alone above.
+// every variant forced through the tuning hook): 64 threads below 2048 floats (a 1280-float row is five full steps of
+// a 64-thread CTA, three ragged ones of a 128-thread CTA: fused min/max 266 -> 219 us), 128 up to 3072, 256 up to
+// 12288, 512 up to 24576, 1024 beyond; two rows in flight per CTA up to 4096 floats, the chunk ring alone above.
 // g_tune[1] = longest row with two rows in flight per CTA, g_tune[2] = forced CTA size.
 template <int OP, int BWD>
 static int launch_staged(const Params& P, cudaStream_t s) {
     const int64_t L = P.geo.row_len;
     const int64_t two_max = g_tune[1] >= 0 ? g_tune[1] : kTwoStageMaxRow;
     const bool two = L <= two_max && L <= 24576;
-    int T = L <= 3072 ? 128 : L <= 12288 ? 256 : L <= 24576 ? 512 : 1024;
+    int T = L < 2048 ? 64 : L <= 3072 ? 128 : L <= 12288 ? 256 : L <= 24576 ? 512 : 1024;
     if (g_tune[2] > 0) T = (int)g_tune[2];
     if (two) {
         if (T <= 64) return launch_staged_inst<OP, BWD, 2, 64>(P, s);
@@ -236,11 +237,11 @@ static int launch_staged(const Params& P, cudaStream_t s) {
 
 template <int OP, int BWD>
 static int launch_block(const Params& P, cudaStream_t s) {
-    // the warp-per-row two-pass variant only wins for the centroid op on rows below 2048 floats (115 vs 138 us at
-    // 1280); the ops the staged kernel does not implement (stats / scale / stochastic) keep their round-1 thresholds
+    // the staged ring wins or ties at every row length for the ops it implements (profiles/block_path_r2_variants.md);
+    // the ops it does not implement (stats / scale / stochastic) keep the round-1 warp two-pass / whole-row staging
     constexpr bool kStagedOp = (OP == OP_UNIFORM || OP == OP_NONUNIFORM);
     const bool staged_ok = kStagedOp && !P.stochastic;
-    const int64_t warp2_default = !staged_ok ? 2 * kWarpTwoPassMaxRow : (OP == OP_NONUNIFORM ? kWarpTwoPassMaxRow - 1 : 0);
+    const int64_t warp2_default = !staged_ok ? 2 * kWarpTwoPassMaxRow : 0;
     const int64_t warp2_max = g_tune[0] >= 0 ? g_tune[0] : warp2_default;
     if (P.geo.row_len <= warp2_max) return launch_block_inst<OP, BWD, false, 32>(P, s);               // warp per row, two passes
     if constexpr (kStagedOp) {
