@@ -108,11 +108,18 @@ def require_cuda() -> None:
 
 
 def ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    # a plain int is accepted for a c_void_p argument: no ctypes object per pointer on the per-call path
+    return None if t is None else t.data_ptr()
 
 
 def stream_ptr(device=None):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def needs_workspace(n: int, bucket: int) -> bool:
+    """Only rows beyond the staging limit (grid path: bucket None / huge buckets on big tensors) use the
+    caller's scratch in the forward ops; everything else runs on chip."""
+    return (bucket == 0 or bucket > MAX_STAGED_BUCKET) and n > MAX_STAGED_BUCKET
 
 
 _ws = {}

@@ -132,6 +132,14 @@ extern "C" size_t qd_workspace_bytes(int64_t n, int64_t bucket) {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- tuning hook (benchmarks only): -1 = built-in choice; keys are listed where they are used ----
+static int64_t g_tune[4] = {-1, -1, -1, -1};
+extern "C" int qd_debug_set_tuning(int key, int64_t value) {
+    if (key < 0 || key >= 4) return fail(QD_ERR_INVALID_ARG, "unknown tuning key %d", key);
+    g_tune[key] = value;
+    return QD_OK;
+}
+
 // ------------------------------------------------------------------ launchers
 template <int OP, int BWD, int R, bool VEC>
 static int launch_warp_inst(const Params& P, cudaStream_t s) {
@@ -143,6 +151,14 @@ static int launch_warp_inst(const Params& P, cudaStream_t s) {
     int64_t need = (P.geo.rows + kWarpsPerCta - 1) / kWarpsPerCta;
     int64_t cap = (int64_t)di->sms * occ;
     int grid = (int)(need < cap ? need : cap);
+    if constexpr (OP == OP_UNIFORM && BWD == (int)BWD_MINMAX && R == 2 && VEC) {
+        if (g_tune[3] == 1) {  // A/B of the r_b accumulation on the headline kernel (tools/headline_ab.py)
+            auto kern_a = warp_rows_kernel<OP, BWD, R, VEC, true>;
+            kern_a<<<grid, kWarpCtaThreads, 0, s>>>(P);
+            QD_CUDA(cudaGetLastError());
+            return QD_OK;
+        }
+    }
     kern<<<grid, kWarpCtaThreads, 0, s>>>(P);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
@@ -176,16 +192,11 @@ static int launch_block_inst(const Params& P, cudaStream_t s) {
     return QD_OK;
 }
 
-// ---- tuning hook (benchmarks only): -1 = built-in choice ----------------------------------
+// tuning keys of the block path:
 //   key 0: longest row (floats) handled by the warp-per-row two-pass variant of the block path
 //   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path
-//   key 2: CTA size of the staged path (128 / 256 / 512 / 1024), 0 or -1 = by row length
-static int64_t g_tune[4] = {-1, -1, -1, -1};
-extern "C" int qd_debug_set_tuning(int key, int64_t value) {
-    if (key < 0 || key >= 4) return fail(QD_ERR_INVALID_ARG, "unknown tuning key %d", key);
-    g_tune[key] = value;
-    return QD_OK;
-}
+//   key 2: CTA size of the staged path (64 / 128 / 256 / 512 / 1024), 0 or -1 = by row length
+//   key 3: 1 = headline kernel accumulates r_b with one float64 add per element (A/B measurement)
 
 // CTA per row, TMA chunk ring (qd_staged_path.cuh)
 template <int OP, int BWD, int STAGES, int T>

@@ -124,7 +124,9 @@ __device__ __forceinline__ void warp_load_row(const Params& P, int64_t row, int 
     if constexpr (BWD != BWD_OFF) load_row<R, VEC, FULL>(P.g + base, len, lane, gv);
 }
 
-template <int OP, int AUX, int R, bool VEC, bool FULL>
+// ACC_A: A/B switch of the r_b accumulation of the min/max backward (benchmarks only, qd_debug_set_tuning key 3):
+// false = minmax_lane_sum (division mode hoisted, float32 groups), true = one float64 add per element
+template <int OP, int AUX, int R, bool VEC, bool FULL, bool ACC_A = false>
 __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroids& cen, const LaneTable<OP, AUX>& rt, int64_t row,
                                                  int lane, float (&v)[4 * R], float (&gv)[4 * R]) {
     constexpr int BWD = (OP == OP_UNIFORM) ? AUX : (int)BWD_OFF;
@@ -277,8 +279,19 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
             int imax = first_equal<R, VEC, FULL>(qv, qmx, len, lane);
             // r_b = sum_j v_j: float32 inside a 128-bit group, float64 across groups, lanes and (fixed tree) the warp
             const RowDivider div2(rs.alpha2);
-            const double acc = div2.ok ? minmax_lane_sum<R, VEC, FULL, true>(v, qv, gv, rs.beta2, rs.alpha2, div2, len, lane)
-                                       : minmax_lane_sum<R, VEC, FULL, false>(v, qv, gv, rs.beta2, rs.alpha2, div2, len, lane);
+            double acc;
+            if constexpr (ACC_A) {
+                acc = 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (FULL || elem_index<R, VEC>(r, j, lane) < len)
+                            acc += (double)minmax_term(v[4 * r + j], qv[4 * r + j], gv[4 * r + j], rs.beta2, div2);
+            } else {
+                acc = div2.ok ? minmax_lane_sum<R, VEC, FULL, true>(v, qv, gv, rs.beta2, rs.alpha2, div2, len, lane)
+                              : minmax_lane_sum<R, VEC, FULL, false>(v, qv, gv, rs.beta2, rs.alpha2, div2, len, lane);
+            }
             const float rb = (float)warp_sum(acc);
             if (imin != imax) {  // +r at argmax', -r at argmin' (the +1/-1 columns of grad_alpha, :380-393)
 #pragma unroll
@@ -360,12 +373,12 @@ __device__ __forceinline__ void warp_compute_row(const Params& P, const Centroid
     }
 }
 
-template <int OP, int AUX, int R, bool VEC, bool FULL>
+template <int OP, int AUX, int R, bool VEC, bool FULL, bool ACC_A = false>
 __device__ __forceinline__ void warp_process_row(const Params& P, const Centroids& cen, const LaneTable<OP, AUX>& rt, int64_t row,
                                                  int lane) {
     float v[4 * R], gv[4 * R];
     warp_load_row<OP, AUX, R, VEC, FULL>(P, row, lane, v, gv);
-    warp_compute_row<OP, AUX, R, VEC, FULL>(P, cen, rt, row, lane, v, gv);
+    warp_compute_row<OP, AUX, R, VEC, FULL, ACC_A>(P, cen, rt, row, lane, v, gv);
 }
 
 // Forward-only ops move 8-9 B/elt and, once the divisions were gone, were limited by the
@@ -384,7 +397,7 @@ constexpr int kMinCtas = (OP == OP_UNIFORM && R == 2 && (AUX == (int)BWD_OFF || 
                          : (OP == OP_UNIFORM && R == 8 && AUX != (int)BWD_OFF) ? 2   // 1024-element rows with a gradient: cap at 128 regs
                                                                                : 0;
 
-template <int OP, int AUX, int R, bool VEC>
+template <int OP, int AUX, int R, bool VEC, bool ACC_A = false>
 __global__ void __launch_bounds__(kWarpCtaThreads, kMinCtas<OP, AUX, R>) warp_rows_kernel(const __grid_constant__ Params P) {
     __shared__ float s_k[OP == OP_NONUNIFORM ? 256 : 1];
     __shared__ float s_t[OP == OP_NONUNIFORM ? 256 : 1];
@@ -418,10 +431,10 @@ __global__ void __launch_bounds__(kWarpCtaThreads, kMinCtas<OP, AUX, R>) warp_ro
                 }
             }
         } else {
-            for (; row < full_rows; row += stride) warp_process_row<OP, AUX, R, true, true>(P, cen, rt, row, lane);
+            for (; row < full_rows; row += stride) warp_process_row<OP, AUX, R, true, true, ACC_A>(P, cen, rt, row, lane);
         }
     }
-    for (; row < P.geo.rows; row += stride) warp_process_row<OP, AUX, R, VEC, false>(P, cen, rt, row, lane);
+    for (; row < P.geo.rows; row += stride) warp_process_row<OP, AUX, R, VEC, false, ACC_A>(P, cen, rt, row, lane);
 }
 
 }  // namespace qd

@@ -110,11 +110,12 @@ class ScalingFunction(object):
         rows, row_len, padded = N.geometry(n, _bucket_arg(self.bucket_size))
         dev = x.device
         stat_shape = (rows, 1) if self.bucket_size is not None else (1,)
-        ab = torch.empty((2,) + stat_shape, dtype=torch.float32, device=dev)       # one allocation for alpha and beta
-        self.alpha, self.beta = ab[0], ab[1]
+        # ONE allocation for alpha, beta (float32) and argmin, argmax (int64, 8-byte aligned behind them)
+        state = torch.empty(rows * (6 if want_arg else 2), dtype=torch.float32, device=dev)
+        self.alpha, self.beta = state[:rows].view(stat_shape), state[rows:2 * rows].view(stat_shape)
         if want_arg:
-            mm = torch.empty((2,) + stat_shape, dtype=torch.int64, device=dev)
-            self.idx_min_rows, self.idx_max_rows = mm[0], mm[1]
+            mm = state[2 * rows:].view(torch.int64)
+            self.idx_min_rows, self.idx_max_rows = mm[:rows].view(stat_shape), mm[rows:].view(stat_shape)
         self.original_tensor_length = n
         self.expected_tensor_size = torch.Size((rows, row_len)) if self.bucket_size is not None else torch.Size((n,))
         self._mean_dev = _mean_tensor(x, self.subtract_mean)
@@ -256,17 +257,20 @@ def uniformQuantization(tensor, s, type_of_scaling="linear", stochastic_rounding
     in_place = modify_in_place and not was_cpu and x.data_ptr() == tensor.data_ptr()
     q = x if in_place else torch.empty_like(x)
     b = _bucket_arg(bucket_size)
-    ws = N.workspace(x.numel(), b, x.device)
+    ws = N.workspace(x.numel(), b, x.device) if N.needs_workspace(x.numel(), b) else None     # grid path only
     seed = offset = 0
     if stochastic_rounding:
         # one Philox stream per call, keyed from torch's default (host) generator so that
         # torch.manual_seed controls it (the reference draws torch.rand on the host, :185)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-    N.check(N.lib().qd_uniform_fwd(N.ptr(x), N.ptr(q), None, N.ptr(scaling_function.alpha), N.ptr(scaling_function.beta),
-                                   N.ptr(scaling_function.idx_min_rows), N.ptr(scaling_function.idx_max_rows), x.numel(),
-                                   b, int(s), N.ptr(scaling_function._mean_dev), _max_element_arg(max_element),
-                                   1 if stochastic_rounding else 0, seed, offset, N.ptr(ws), ws.numel(),
-                                   N.stream_ptr(x.device)))
+    rc = N.lib().qd_uniform_fwd(x.data_ptr(), q.data_ptr(), None, scaling_function.alpha.data_ptr(),
+                                scaling_function.beta.data_ptr(), scaling_function.idx_min_rows.data_ptr(),
+                                scaling_function.idx_max_rows.data_ptr(), x.numel(), b, int(s),
+                                N.ptr(scaling_function._mean_dev), _max_element_arg(max_element),
+                                1 if stochastic_rounding else 0, seed, offset, N.ptr(ws), ws.numel() if ws is not None else 0,
+                                N.stream_ptr(x.device))
+    if rc:
+        N.check(rc)
     q = q.view(tensor.size())
     if was_cpu:
         q = q.cpu()
