@@ -235,7 +235,8 @@ int qd_uniform_fwd_bwd_host(const float* x_host, const float* g_host, float* q_h
  *   key 0: longest row (floats) taken by the warp-per-row two-pass variant
  *   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path
  *   key 2: threads per CTA of the staged path (64 / 128 / 256 / 512 / 1024)
- *   key 3: 1 = fused min/max kernel (bucket <= 256) sums r_b with one float64 add per element (A/B measurement) */
+ *   key 3: warp-path min/max backward sums r_b per element in float64 (1) or in float32 groups of four (0);
+ *          built-in choice: per element when q is written in the same pass, grouped for the backward alone */
 int qd_debug_set_tuning(int key, int64_t value);
 
 /* ---- self tests used by tests/ (device side arithmetic checks) ---------- */

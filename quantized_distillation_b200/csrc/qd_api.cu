@@ -151,8 +151,13 @@ static int launch_warp_inst(const Params& P, cudaStream_t s) {
     int64_t need = (P.geo.rows + kWarpsPerCta - 1) / kWarpsPerCta;
     int64_t cap = (int64_t)di->sms * occ;
     int grid = (int)(need < cap ? need : cap);
-    if constexpr (OP == OP_UNIFORM && BWD == (int)BWD_MINMAX && R == 2 && VEC) {
-        if (g_tune[3] == 1) {  // A/B of the r_b accumulation on the headline kernel (tools/headline_ab.py)
+    if constexpr (OP == OP_UNIFORM && BWD == (int)BWD_MINMAX) {
+        // r_b accumulation, measured A/B on one box (tools/headline_ab.py, 200 back-to-back launches, 64 Mi floats):
+        // fused forward+backward 173-178 us with one float64 add per element vs 184-192 us with the grouped lane sum;
+        // backward alone 158-167 us vs 139-146 us.  So the variant follows the presence of the q output
+        // (key 3: 1 forces the per-element sum, 0 the grouped one).
+        const bool per_element = g_tune[3] >= 0 ? (g_tune[3] == 1) : (P.q != nullptr);
+        if (per_element) {
             auto kern_a = warp_rows_kernel<OP, BWD, R, VEC, true>;
             kern_a<<<grid, kWarpCtaThreads, 0, s>>>(P);
             QD_CUDA(cudaGetLastError());

@@ -110,12 +110,11 @@ class ScalingFunction(object):
         rows, row_len, padded = N.geometry(n, _bucket_arg(self.bucket_size))
         dev = x.device
         stat_shape = (rows, 1) if self.bucket_size is not None else (1,)
-        # ONE allocation for alpha, beta (float32) and argmin, argmax (int64, 8-byte aligned behind them)
-        state = torch.empty(rows * (6 if want_arg else 2), dtype=torch.float32, device=dev)
-        self.alpha, self.beta = state[:rows].view(stat_shape), state[rows:2 * rows].view(stat_shape)
+        ab = torch.empty((2,) + stat_shape, dtype=torch.float32, device=dev)       # one allocation for alpha and beta
+        self.alpha, self.beta = ab[0], ab[1]
         if want_arg:
-            mm = state[2 * rows:].view(torch.int64)
-            self.idx_min_rows, self.idx_max_rows = mm[:rows].view(stat_shape), mm[rows:].view(stat_shape)
+            mm = torch.empty((2,) + stat_shape, dtype=torch.int64, device=dev)
+            self.idx_min_rows, self.idx_max_rows = mm[0], mm[1]
         self.original_tensor_length = n
         self.expected_tensor_size = torch.Size((rows, row_len)) if self.bucket_size is not None else torch.Size((n,))
         self._mean_dev = _mean_tensor(x, self.subtract_mean)

@@ -310,7 +310,16 @@ def test_fused_fwd_bwd_capi(Q):
             assert_same(q.cpu().numpy(), qref, f"fused q mode {mode}")
             go2 = torch.empty_like(g)
             N.check(N.lib().qd_uniform_bwd(N.ptr(x), N.ptr(g), N.ptr(go2), n, b, 16, mode, N.ptr(ws), ws.numel(), N.stream_ptr()))
-            assert_same(go.cpu().numpy(), go2.cpu().numpy(), f"fused gout mode {mode}")
+            if mode == N.BWD_MINMAX:
+                # the fused pass and the stand-alone backward may add the terms of r_b in a different order (each uses
+                # the faster one, qd_api.cu): same positions, both inside the a5 tolerance of the oracle
+                ref, info = O.uniform_bwd_minmax(x.cpu().numpy(), g.cpu().numpy(), 16, b)
+                for out in (go, go2):
+                    assert_minmax_gradient(out.cpu().numpy(), g.cpu().numpy(), ref, info["argmax"], info["argmin"], info["abs_sum"],
+                                           info["r"], f"fused/unfused min/max n={n} b={b}")
+                assert np.array_equal(np.nonzero((go != g).cpu().numpy())[0], np.nonzero((go2 != g).cpu().numpy())[0])
+            else:
+                assert_same(go.cpu().numpy(), go2.cpu().numpy(), f"fused gout mode {mode}")
             if mode == N.BWD_STE:
                 assert_same(go.cpu().numpy(), g.cpu().numpy(), "ste")
             if mode == N.BWD_TRUNCATED:

@@ -40,7 +40,7 @@ def sample(mode, launches=200):
 
 out = {"fused_minmax_us": {"A": [], "B": []}, "bwd_minmax_alone_us": {"A": [], "B": []}, "fused_ste_us": []}
 for rep in range(4):
-    for name, v in (("B", -1), ("A", 1)):
+    for name, v in (("B", 0), ("A", 1)):
         N.check(lib.qd_debug_set_tuning(3, v))
         out["fused_minmax_us"][name].append(round(sample(N.BWD_MINMAX), 2))
         out["bwd_minmax_alone_us"][name].append(round(sample(None), 2))
