@@ -677,13 +677,14 @@ extern "C" int qd_index_histogram(const uint8_t* idx_u8, int64_t n, int num_bins
 }
 
 // ------------------------------------------------------------------ f2: packed codec
-// one thread = 8 consecutive codes in (one 64-bit load), `bits` bytes out (one store of that width)
-__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ idx, uint8_t* __restrict__ packed, int64_t n,
-                                                  int bits) {
+// one thread = 8 consecutive codes in (one 64-bit load), BITS bytes out (one store of that width); BITS is a
+// template parameter so that every shift, mask and access width is a compile-time constant
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ idx, uint8_t* __restrict__ packed, int64_t n) {
     const int64_t groups = (n + 7) / 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const unsigned mask = (1u << bits) - 1u;
-    const int64_t out_bytes = (n * bits + 7) / 8;
+    constexpr unsigned mask = (1u << BITS) - 1u;
+    const int64_t out_bytes = (n * BITS + 7) / 8;
     const bool in_vec = (reinterpret_cast<uintptr_t>(idx) & 7) == 0;
     const bool out_vec = (reinterpret_cast<uintptr_t>(packed) & 7) == 0;
     for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += stride) {
@@ -697,16 +698,16 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ i
         }
         unsigned long long word = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) word |= (unsigned long long)((unsigned)(codes >> (8 * j)) & mask) << (j * bits);
-        uint8_t* dst = packed + gidx * bits;
-        if (out_vec && (gidx + 1) * bits <= out_bytes) {
-            if (bits == 8) *reinterpret_cast<unsigned long long*>(dst) = word;
-            else if (bits == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)word;
-            else if (bits == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word;
+        for (int j = 0; j < 8; ++j) word |= (unsigned long long)((unsigned)(codes >> (8 * j)) & mask) << (j * BITS);
+        uint8_t* dst = packed + gidx * BITS;
+        if (out_vec && (gidx + 1) * BITS <= out_bytes) {
+            if constexpr (BITS == 8) *reinterpret_cast<unsigned long long*>(dst) = word;
+            else if constexpr (BITS == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)word;
+            else if constexpr (BITS == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word;
             else *dst = (uint8_t)word;
         } else {
-            for (int b = 0; b < bits; ++b)
-                if (gidx * bits + b < out_bytes) dst[b] = (uint8_t)(word >> (8 * b));
+            for (int b = 0; b < BITS; ++b)
+                if (gidx * BITS + b < out_bytes) dst[b] = (uint8_t)(word >> (8 * b));
         }
     }
 }
@@ -719,16 +720,20 @@ extern "C" int qd_pack_indices(const uint8_t* idx_u8, uint8_t* packed, int64_t n
     if (rc) return rc;
     int64_t need = ((n + 7) / 8 + 255) / 256;
     int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
-    pack_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx_u8, packed, n, bits);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (bits == 8) pack_kernel<8><<<grid, 256, 0, s>>>(idx_u8, packed, n);
+    else if (bits == 4) pack_kernel<4><<<grid, 256, 0, s>>>(idx_u8, packed, n);
+    else if (bits == 2) pack_kernel<2><<<grid, 256, 0, s>>>(idx_u8, packed, n);
+    else pack_kernel<1><<<grid, 256, 0, s>>>(idx_u8, packed, n);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
 
-// one thread = FOUR consecutive elements: their codes sit in at most four bytes starting at byte 4*g*bits/8, the
-// four dequantized values leave as one 128-bit store (a warp writes 512 contiguous bytes); the row of a group
+// one thread = FOUR consecutive elements: their codes are one aligned load of 4*BITS bits (a nibble for BITS = 1),
+// the four dequantized values leave as one 128-bit store (a warp writes 512 contiguous bytes); the row of a group
 // advances by a fixed step per iteration (no division per element)
-template <bool UNIFORM>
-__global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __restrict__ packed, int bits,
+template <bool UNIFORM, int BITS>
+__global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __restrict__ packed,
                                                             const float* __restrict__ points, int K,
                                                             const float* __restrict__ alpha, const float* __restrict__ beta,
                                                             float* __restrict__ q, Geometry geo, float S, float rS) {
@@ -739,10 +744,12 @@ __global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __re
     }
     const int64_t groups = (geo.n + 3) / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const unsigned mask = (1u << bits) - 1u;
-    const int64_t in_bytes = (geo.n * bits + 7) / 8;
+    constexpr unsigned mask = (1u << BITS) - 1u;
+    const int64_t in_bytes = (geo.n * BITS + 7) / 8;
     const bool ovec = (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+    const bool ivec = (reinterpret_cast<uintptr_t>(packed) & 3) == 0;
     const bool same_row = geo.rows == 1 || geo.row_len % 4 == 0;   // the four elements of a group share their row
+    const bool small_s = S <= 255.0f;
     const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t row = (geo.rows == 1) ? 0 : (g0 * 4) / geo.row_len;
     int64_t rem = (geo.rows == 1) ? 0 : (g0 * 4) - row * geo.row_len;
@@ -750,21 +757,28 @@ __global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __re
     const int64_t step_rem = (geo.rows == 1) ? 0 : (stride * 4) - step_rows * geo.row_len;
     for (int64_t gidx = g0; gidx < groups; gidx += stride) {
         const int64_t e0 = gidx * 4;
-        const int64_t bit0 = e0 * bits;
-        const int64_t b0 = bit0 >> 3;
-        uint32_t word = 0;
-        const int nbytes = (4 * bits + (int)(bit0 & 7) + 7) >> 3;   // 1 (bits 1, 2), 2 (bits 4) or 4 (bits 8)
-        for (int b = 0; b < nbytes; ++b)
-            if (b0 + b < in_bytes) word |= (uint32_t)packed[b0 + b] << (8 * b);
-        word >>= (unsigned)(bit0 & 7);
+        uint32_t word;
+        if constexpr (BITS == 8) {
+            const int64_t b0 = e0;
+            if (ivec && b0 + 4 <= in_bytes) word = *reinterpret_cast<const uint32_t*>(packed + b0);
+            else { word = 0; for (int b = 0; b < 4; ++b) if (b0 + b < in_bytes) word |= (uint32_t)packed[b0 + b] << (8 * b); }
+        } else if constexpr (BITS == 4) {
+            const int64_t b0 = e0 >> 1;
+            if (ivec && b0 + 2 <= in_bytes) word = *reinterpret_cast<const uint16_t*>(packed + b0);
+            else { word = packed[b0]; if (b0 + 1 < in_bytes) word |= (uint32_t)packed[b0 + 1] << 8; }
+        } else if constexpr (BITS == 2) {
+            word = packed[e0 >> 2];
+        } else {
+            word = (uint32_t)packed[e0 >> 3] >> (unsigned)(e0 & 4);
+        }
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const unsigned c = (word >> (j * bits)) & mask;
+            const unsigned c = (word >> (j * BITS)) & mask;
             int64_t r = row;
-            if (!same_row) r = (e0 + j) / geo.row_len;
-            const float unit = UNIFORM ? ((S <= 255.0f) ? small_level_to_unit((float)c, S, rS) : level_to_unit((float)c, S)) : s_pts[c];
-            o[j] = (e0 + j < geo.n) ? from_unit(unit, alpha[r], beta[r]) : 0.f;
+            if (!same_row) r = (e0 + j < geo.n) ? (e0 + j) / geo.row_len : row;
+            const float unit = UNIFORM ? (small_s ? small_level_to_unit((float)c, S, rS) : level_to_unit((float)c, S)) : s_pts[c];
+            o[j] = from_unit(unit, alpha[r], beta[r]);
         }
         if (ovec && e0 + 4 <= geo.n) {
             st_stream4(q + e0, make_float4(o[0], o[1], o[2], o[3]));
@@ -799,8 +813,11 @@ extern "C" int qd_unpack_dequant_uniform(const uint8_t* packed, int bits, const 
     int rc = unpack_common(packed, bits, alpha, beta, q, n, bucket, &geo, &grid);
     if (rc) return rc;
     const float S = (float)(levels - 1);
-    unpack_dequant_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, bits, nullptr, 0, alpha, beta,
-                                                                                        q, geo, S, 1.0f / S);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bits == 8) unpack_dequant_kernel<true, 8><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
+    else if (bits == 4) unpack_dequant_kernel<true, 4><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
+    else if (bits == 2) unpack_dequant_kernel<true, 2><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
+    else unpack_dequant_kernel<true, 1><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
@@ -813,8 +830,11 @@ extern "C" int qd_unpack_dequant_nonuniform(const uint8_t* packed, int bits, con
     if (points == nullptr || num_points < 1 || num_points > (1 << bits)) return fail(QD_ERR_INVALID_ARG, "num_points must be in [1, 2^bits]");
     int rc = unpack_common(packed, bits, alpha, beta, q, n, bucket, &geo, &grid);
     if (rc) return rc;
-    unpack_dequant_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, bits, points, num_points,
-                                                                                         alpha, beta, q, geo, 0.f, 0.f);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bits == 8) unpack_dequant_kernel<false, 8><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
+    else if (bits == 4) unpack_dequant_kernel<false, 4><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
+    else if (bits == 2) unpack_dequant_kernel<false, 2><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
+    else unpack_dequant_kernel<false, 1><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
