@@ -133,9 +133,9 @@ extern "C" size_t qd_workspace_bytes(int64_t n, int64_t bucket) {
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- tuning hook (benchmarks only): -1 = built-in choice; keys are listed where they are used ----
-static int64_t g_tune[4] = {-1, -1, -1, -1};
+static int64_t g_tune[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
 extern "C" int qd_debug_set_tuning(int key, int64_t value) {
-    if (key < 0 || key >= 4) return fail(QD_ERR_INVALID_ARG, "unknown tuning key %d", key);
+    if (key < 0 || key >= 8) return fail(QD_ERR_INVALID_ARG, "unknown tuning key %d", key);
     g_tune[key] = value;
     return QD_OK;
 }
@@ -297,10 +297,16 @@ static bool rows_vectorizable(const Params& P) {
     return ptrs && (P.geo.rows == 1 || (P.geo.row_len % 4) == 0);
 }
 
+// longest row the register-resident warp path takes for (OP, BWD); set from profiles/block_path_r2_small_rows.md
+template <int OP, int BWD>
+static constexpr int64_t warp_path_max_row() { return 1024; }
+
 template <int OP, int BWD>
 static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) {
     if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
-    if (P.geo.row_len <= 1024) return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
+    // longest row of the register-resident warp path (key 4 of the tuning hook moves the border for measurements)
+    const int64_t warp_max = (g_tune[4] >= 0 && g_tune[4] <= 1024) ? g_tune[4] : warp_path_max_row<OP, BWD>();
+    if (P.geo.row_len <= warp_max) return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
     // the CTA / grid paths keep stochastic rounding as a run-time branch of OP_UNIFORM
     constexpr int OP2 = (OP == OP_UNIFORM_STOCH) ? OP_UNIFORM : OP;
     if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP2, BWD>(P, s);
@@ -524,7 +530,8 @@ extern "C" int qd_nonuniform_fwd(const float* x, const float* points, int num_po
     P.x = x; P.q = q; P.idx8 = idx_u8; P.idx64 = idx_i64; P.alpha = alpha; P.beta = beta;
     P.points = points; P.num_points = num_points; P.rule = rule; P.mean = mean; P.max_element = max_element;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (P.geo.row_len <= 1024) {  // warp path: short centroid tables live in registers (AUX = table size)
+    const int64_t warp_max = (g_tune[4] >= 0 && g_tune[4] <= 1024) ? g_tune[4] : warp_path_max_row<OP_NONUNIFORM, BWD_OFF>();
+    if (P.geo.row_len <= warp_max) {  // warp path: centroid tables of up to 32 points live in the lanes (AUX = table size class)
         const bool vec = rows_vectorizable(P);
         if (num_points <= 4) return launch_warp<OP_NONUNIFORM, 4>(P, vec, s);     // <= 32: table in the lanes (LaneSearch)
         if (num_points <= 8) return launch_warp<OP_NONUNIFORM, 8>(P, vec, s);

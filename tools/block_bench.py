@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "block_path.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--small", action="store_true", help="rows of 384 .. 1024 floats: warp path vs staged ring (tuning key 4)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib, sp = N.lib(), N.stream_ptr(dev)
@@ -51,6 +52,8 @@ def main():
         N.check(lib.qd_debug_set_tuning(key, value))
 
     rows = []
+    if args.small:
+        return small_rows(args, lib, sp, dev, peak, n, x, g, q, go, idx, pts4, pts16, timed, tune)
     buckets = (1280, 1536, 2048) if args.quick else (1280, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152)
     for bucket in buckets:
         ws = N.workspace(n, bucket, dev)
@@ -106,6 +109,39 @@ def main():
                 if any(c != "-" for c in cells):
                     f.write(f"| {b} | {v} | " + " | ".join(cells) + " |\n")
     print("wrote", args.out)
+
+
+def small_rows(args, lib, sp, dev, peak, n, x, g, q, go, idx, pts4, pts16, timed, tune):
+    """Rows the warp path keeps in registers (R = 4: <= 512, R = 8: <= 1024) against the staged ring forced down to them."""
+    rows = []
+    for bucket in (384, 512, 768, 1024):
+        ws = N.workspace(n, bucket, dev)
+        ops = {
+            "uniform_fwd": (8, lambda: N.check(lib.qd_uniform_fwd(N.ptr(x), N.ptr(q), None, None, None, None, None, n, bucket, 16, None, 0.0, 0, 0, 0, N.ptr(ws), ws.numel(), sp))),
+            "fused_ste": (16, lambda: N.check(lib.qd_uniform_fwd_bwd(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, bucket, 16, N.BWD_STE, N.ptr(ws), ws.numel(), sp))),
+            "fused_minmax": (16, lambda: N.check(lib.qd_uniform_fwd_bwd(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, bucket, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(), sp))),
+            "bwd_minmax": (12, lambda: N.check(lib.qd_uniform_bwd(N.ptr(x), N.ptr(g), N.ptr(go), n, bucket, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(), sp))),
+            "nonuniform_K4_mid": (9, lambda: N.check(lib.qd_nonuniform_fwd(N.ptr(x), N.ptr(pts4), 4, N.RULE_MIDPOINT, N.ptr(q), N.ptr(idx), None, None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp))),
+            "nonuniform_K16_near": (9, lambda: N.check(lib.qd_nonuniform_fwd(N.ptr(x), N.ptr(pts16), 16, N.RULE_NEAREST, N.ptr(q), N.ptr(idx), None, None, None, n, bucket, None, 0.0, N.ptr(ws), ws.numel(), sp))),
+        }
+        for vname, key4 in (("warp", -1), ("staged_t64", 256)):
+            tune(4, key4)
+            for oname, (bpe, fn) in ops.items():
+                sec = timed(fn)
+                gbs = n * bpe / sec / 1e9
+                rows.append({"bucket": bucket, "variant": vname, "op": oname, "us": round(sec * 1e6, 1), "frac_measured_peak": round(gbs / peak, 3)})
+        tune(4, -1)
+        print(f"bucket {bucket:5d}: " + " | ".join(f"{o} " + "/".join(f"{r['variant']}={r['us']:.0f}" for r in rows if r["bucket"] == bucket and r["op"] == o) for o in ops), flush=True)
+    out = args.out.replace(".json", "_small_rows.json")
+    json.dump({"rows": rows}, open(out, "w"), indent=1)
+    with open(out.replace(".json", ".md"), "w") as f:
+        opn = list(dict.fromkeys(r["op"] for r in rows))
+        f.write("64 Mi float32, levels 16; microseconds per launch (fraction of the measured HBM peak)\n\n| bucket | variant | " + " | ".join(opn) + " |\n|---|---|" + "---|" * len(opn) + "\n")
+        for b in (384, 512, 768, 1024):
+            for v in ("warp", "staged_t64"):
+                cells = [next(f"{r['us']:.0f} ({r['frac_measured_peak']:.2f})" for r in rows if r["bucket"] == b and r["variant"] == v and r["op"] == o) for o in opn]
+                f.write(f"| {b} | {v} | " + " | ".join(cells) + " |\n")
+    print("wrote", out)
 
 
 if __name__ == "__main__":
