@@ -306,7 +306,12 @@ static int run_rows(const Params& P, void* ws, size_t ws_bytes, cudaStream_t s) 
     if (P.geo.row_len >= (int64_t)1 << 31) return fail(QD_ERR_UNSUPPORTED, "rows of 2^31 elements or more are not supported");
     // longest row of the register-resident warp path (key 4 of the tuning hook moves the border for measurements)
     const int64_t warp_max = (g_tune[4] >= 0 && g_tune[4] <= 1024) ? g_tune[4] : warp_path_max_row<OP, BWD>();
-    if (P.geo.row_len <= warp_max) return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
+    // ragged rows of 513..1023 floats with the min/max backward: the R = 8 register kernel runs its predicated
+    // (non-FULL) variant at 128 registers there -- 425 us at 768 floats against 249 us on the staged ring
+    // (profiles/block_path_r2_small_rows.md); everything else up to 1024 floats is faster in registers
+    const bool ragged_minmax = OP == OP_UNIFORM && BWD == (int)BWD_MINMAX && P.geo.row_len > 512 && P.geo.row_len < 1024 && g_tune[4] < 0;
+    if (P.geo.row_len <= warp_max && !ragged_minmax)
+        return launch_warp<OP, (OP == OP_NONUNIFORM ? 256 : BWD)>(P, rows_vectorizable(P), s);
     // the CTA / grid paths keep stochastic rounding as a run-time branch of OP_UNIFORM
     constexpr int OP2 = (OP == OP_UNIFORM_STOCH) ? OP_UNIFORM : OP;
     if (P.geo.row_len <= QD_MAX_STAGED_BUCKET) return launch_block<OP2, BWD>(P, s);

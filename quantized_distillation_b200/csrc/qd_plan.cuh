@@ -285,21 +285,10 @@ __global__ void __launch_bounds__(kPgThreads) plan_points_grad_partial(const NuE
             }
             if (++since_flush == kPgFlushEvery) {  // float32 columns only ever add a few hundred terms
                 since_flush = 0;
-                __syncwarp();
-                for (int k = 0; k < K; ++k) {
-                    const double s = warp_sum((double)col[k][lane]);
-                    col[k][lane] = 0.f;
-                    if (lane == k) acc += s;
-                }
-                __syncwarp();
+                acc += flush_column(col, lane, K);
             }
         }
-        __syncwarp();
-        for (int k = 0; k < K; ++k) {
-            const double s = warp_sum((double)col[k][lane]);
-            if (lane == k) acc += s;
-        }
-        __syncwarp();
+        acc += flush_column(col, lane, K);
         if (lane < K) partial[blk * kNuMaxK + lane] = acc;
     }
 }

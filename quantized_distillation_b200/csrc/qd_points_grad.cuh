@@ -24,6 +24,25 @@ constexpr int kPgTile = 1024;      // elements per warp work item
 constexpr int kPgSweep = 32;       // centroids handled per sweep over the data
 constexpr int kPgFlushEvery = 16;  // tiles between float32 -> float64 flushes (<= 512 float32 adds per column)
 
+// float32 -> float64 flush of a warp's columns: lane k (k < kcount) owns centroid k and adds the 32 per-lane
+// partials of its row col[k][0..31], walking them with a lane-dependent skew so that the 32 lanes read 32
+// different banks at every step.  Cost independent of kcount (32 loads + adds per lane) instead of kcount
+// warp-wide float64 reductions; fixed order -> deterministic.  Returns the row sum and clears the row.
+__device__ __forceinline__ double flush_column(float (*col)[32], int lane, int kcount) {
+    __syncwarp();
+    double s = 0.0;
+    if (lane < kcount) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const int jj = (j + lane) & 31;
+            s += (double)col[lane][jj];
+            col[lane][jj] = 0.f;
+        }
+    }
+    __syncwarp();
+    return s;
+}
+
 template <typename IdxT>
 __global__ void __launch_bounds__(kPgThreads) points_grad_partial(const float* __restrict__ g,
                                                                  const IdxT* __restrict__ idx,
@@ -100,16 +119,13 @@ __global__ void __launch_bounds__(kPgThreads) points_grad_partial(const float* _
             }
             if (++since_flush == kPgFlushEvery) {
                 since_flush = 0;
-                for (int k = 0; k < kcount; ++k) {
-                    const double s = warp_sum((double)col[k][lane]);
-                    col[k][lane] = 0.f;
-                    if (lane == 0) s_acc[warp * K + kg + k] += s;
-                }
+                const double s = flush_column(col, lane, kcount);
+                if (lane < kcount) s_acc[warp * K + kg + lane] += s;
             }
         }
-        for (int k = 0; k < kcount; ++k) {
-            const double s = warp_sum((double)col[k][lane]);
-            if (lane == 0) s_acc[warp * K + kg + k] += s;
+        {
+            const double s = flush_column(col, lane, kcount);
+            if (lane < kcount) s_acc[warp * K + kg + lane] += s;
         }
         __syncwarp();
     }

@@ -151,7 +151,7 @@ def test_huffman_golden(Q, golden):
 SIZES = [1, 3, 4, 5, 31, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 4096, 5000, 65536 + 17, 200003]
 # 1026 / 3002: rows alternate between 16-byte aligned and unaligned (bulk-copied vs ld.global-staged rows of
 # the staged path inherit each other's ring slots); 12000: two-chunk rows; 49152: the shared-memory limit
-BUCKETS = [None, 256, 512, 1024, 100, 7, 1026, 2048, 3000, 3002, 4096, 8192, 12000, 20000, 49152]
+BUCKETS = [None, 256, 384, 512, 768, 1024, 100, 7, 1026, 2048, 3000, 3002, 4096, 8192, 12000, 20000, 49152]
 
 
 @pytest.mark.parametrize("bucket", BUCKETS)
@@ -259,7 +259,7 @@ def test_large_level_counts_use_exact_path(Q):
         assert_same(qd.cpu().numpy(), q, f"s={s}")
 
 
-@pytest.mark.parametrize("bucket", [256, 512, 1024, 100, 1026, 2048, 3002, 4096, 8192, 12000, 20000, 49152])
+@pytest.mark.parametrize("bucket", [256, 384, 512, 768, 1000, 1024, 100, 1026, 2048, 3002, 4096, 8192, 12000, 20000, 49152])
 def test_minmax_backward_vs_oracle(Q, bucket):
     rng = np.random.default_rng(5)
     for n in (1, 100, 256, 257, 1000, 4099, 20000, 150001):
