@@ -87,6 +87,32 @@ def lib() -> C.CDLL:
     return _lib
 
 
+_fast = None
+_fast_tried = False
+
+
+def fast():
+    """The optional compiled front door of the per-tensor ops (csrc/qd_torch_fast.cpp, built by
+    build.build_fast() / __graft_entry__.build()): ATen allocation + one C-ABI call from C++ instead of
+    ctypes marshalling.  None when it has not been built -- callers then use the ctypes path; either way the
+    arithmetic happens in libqd_b200.so."""
+    global _fast, _fast_tried
+    if not _fast_tried:
+        _fast_tried = True
+        path = os.path.join(_HERE, "_fastcall", "_qd_fast.so")
+        if os.path.exists(path):
+            try:
+                import importlib.util
+                lib()                                            # libqd_b200.so first: the module links against it
+                spec = importlib.util.spec_from_file_location("_qd_fast", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _fast = mod
+            except Exception:                                    # stale build, other torch: ctypes still works
+                _fast = None
+    return _fast
+
+
 def check(rc: int) -> None:
     """Maps qd_status to the exception type the reference raises for the same
     condition (ValueError / NotImplementedError, quant_functions.py:22-33,

@@ -45,6 +45,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+# ---- optional compiled front door of the per-tensor API (csrc/qd_torch_fast.cpp) ---------------------------------
+FAST_SRC = os.path.join(HERE, "csrc", "qd_torch_fast.cpp")
+FAST_DIR = os.path.join(HERE, "_fastcall")
+FAST_OUT = os.path.join(FAST_DIR, "_qd_fast.so")
+
+
+def fast_is_stale() -> bool:
+    if not os.path.exists(FAST_OUT):
+        return True
+    t = os.path.getmtime(FAST_OUT)
+    return os.path.getmtime(FAST_SRC) > t or os.path.getmtime(os.path.join(ROOT, "include", "qd_b200.h")) > t
+
+
+def build_fast(force: bool = False, verbose: bool = False) -> str:
+    """Compiles the pybind11 / ATen front door against the torch of this interpreter and links it to the in-tree
+    libqd_b200.so.  Host C++ only: no device code, nothing arch specific."""
+    if not force and not fast_is_stale():
+        return FAST_OUT
+    build()                                        # the library it links against
+    from torch.utils import cpp_extension as ce
+    os.makedirs(FAST_DIR, exist_ok=True)
+    ce.load(name="_qd_fast", sources=[FAST_SRC], extra_include_paths=[os.path.join(ROOT, "include")],
+            extra_cflags=["-O2", "-std=c++17"], with_cuda=True,
+            extra_ldflags=[f"-L{HERE}", "-lqd_b200", "-Wl,-rpath," + HERE],      # the loader also pre-loads libqd_b200.so by path
+            build_directory=FAST_DIR, verbose=verbose, is_python_module=False)
+    if not os.path.exists(FAST_OUT):
+        raise RuntimeError("the fast-call module was not produced")
+    return FAST_OUT
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -226,6 +226,20 @@ def uniformQuantization(tensor, s, type_of_scaling="linear", stochastic_rounding
     if modify_in_place and not tensor.is_contiguous():
         raise ValueError("modify_in_place needs a contiguous tensor (the reference's .view(-1) has the same requirement)")
     scaling_function = ScalingFunction(type_of_scaling, max_element, subtract_mean, bucket_size, modify_in_place=True)
+    fast = N.fast()
+    if (fast is not None and tensor.is_cuda and tensor.is_contiguous() and scaling_function.type_scaling == "linear"
+            and not stochastic_rounding and max_element is False and not subtract_mean):
+        # compiled front door: allocation, stream lookup and the C-ABI call happen in C++ (same kernel, same bits)
+        sf = scaling_function
+        n = tensor.numel()
+        q, sf.alpha, sf.beta, sf.idx_min_rows, sf.idx_max_rows = fast.uniform_fwd(tensor, int(s), _bucket_arg(bucket_size),
+                                                                                   bool(modify_in_place))
+        sf.original_tensor_size = tensor.size()
+        sf.original_tensor_length = n
+        sf.expected_tensor_size = torch.Size((sf.alpha.size(0), bucket_size if n >= bucket_size else n)) if bucket_size is not None \
+            else torch.Size((n,))
+        sf.mean_tensor = 0
+        return q, sf
     was_cpu = not tensor.is_cuda
     x = _to_device(tensor)
     scaling_function._was_cpu = was_cpu
@@ -330,6 +344,11 @@ class uniformQuantization_variable(object):
         g = _to_device(grad_output)
         if g.numel() != x.numel():
             raise ValueError("grad_output does not match the saved input")
+        fast = N.fast()
+        if fast is not None and not was_cpu:
+            out = fast.uniform_bwd(x, g, int(self.s), int(self.bucket_size), N.BWD_MINMAX)
+            self.saved_for_backward = None                                               # :404-405
+            return out.view(grad_output.size())
         out = torch.empty_like(g)
         ws = N.workspace(x.numel(), self.bucket_size, x.device)
         N.check(N.lib().qd_uniform_bwd(N.ptr(x), N.ptr(g), N.ptr(out), x.numel(), int(self.bucket_size), int(self.s),

@@ -156,3 +156,17 @@ def test_percentile_plan_is_numpy_percentile():
             ours = np.asarray(H.percentile_combine(o[p], o[nx], g), dtype=np.float64)
             ref = np.asarray(np.percentile(v, np.linspace(0, 100, num=K)), dtype=np.float64)
             assert np.array_equal(ours.view(np.uint64), ref.view(np.uint64)), (n, K)
+
+
+def test_compiled_front_door_builds_and_refuses_cpu_tensors():
+    """csrc/qd_torch_fast.cpp: host-only C++ (pybind11 + ATen) around the C ABI.  It must build against this
+    interpreter's torch, load next to libqd_b200.so, and -- like everything else here -- never compute on the CPU."""
+    import torch
+    from quantized_distillation_b200 import _native as N
+    from quantized_distillation_b200 import build as B
+    B.build_fast()
+    N._fast_tried = False
+    mod = N.fast()
+    assert mod is not None and hasattr(mod, "uniform_fwd") and hasattr(mod, "uniform_bwd")
+    with pytest.raises(RuntimeError):
+        mod.uniform_fwd(torch.zeros(16), 16, 0, False)

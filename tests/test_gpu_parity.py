@@ -734,6 +734,43 @@ def test_absmax_absnorm_extension_matches_the_intended_semantics(Q):
         QF.ALLOW_UNPINNED_SCALING = False
 
 
+def test_compiled_front_door_equals_ctypes_path(Q):
+    """The optional pybind/ATen module in front of the per-tensor ops (csrc/qd_torch_fast.cpp) is plumbing only: with it
+    and without it (ctypes) every output -- q, alpha, beta, argmin, argmax, shapes, dtypes, the backward -- is identical."""
+    from quantized_distillation_b200 import _native as N
+    if N.fast() is None:
+        pytest.skip("fast-call module not built")
+    rng = np.random.default_rng(71)
+    saved = N._fast
+    try:
+        for n, bucket in ((5000, 256), (10, 256), (257, 100), (70001, 1024), (100000, 4096), (300001, None)):
+            x = dev((rng.standard_normal(n) * 0.05).astype(np.float32)).view(-1, 1) if n == 5000 else dev((rng.standard_normal(n) * 0.05).astype(np.float32))
+            g = dev(rng.standard_normal(n).astype(np.float32)).view(x.shape)
+            outs = []
+            for use_fast in (True, False):
+                N._fast = saved if use_fast else None
+                q, sf = Q.uniformQuantization(x, 16, bucket_size=bucket)
+                res = [q, sf.alpha, sf.beta, sf.idx_min_rows, sf.idx_max_rows]
+                meta = (sf.original_tensor_size, sf.original_tensor_length, sf.expected_tensor_size, sf.mean_tensor)
+                if bucket is not None:
+                    f = Q.uniformQuantization_variable(16, bucket_size=bucket)
+                    f.forward(x)
+                    res.append(f.backward(g))
+                outs.append((res, meta))
+            for a, b in zip(outs[0][0], outs[1][0]):
+                assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b)
+            assert outs[0][1] == outs[1][1]
+        N._fast = saved
+        xin = dev((rng.standard_normal(4096) * 0.05).astype(np.float32))
+        keep = xin.clone()
+        q, _ = Q.uniformQuantization(xin, 4, bucket_size=256, modify_in_place=True)
+        assert q.data_ptr() == xin.data_ptr() and not torch.equal(xin, keep)
+        with pytest.raises(ValueError):
+            Q.uniformQuantization(xin, 1, bucket_size=256)                      # levels < 2: the C ABI's INVALID_ARG -> ValueError
+    finally:
+        N._fast = saved
+
+
 def test_error_mapping(Q):
     x = torch.randn(100).cuda()
     with pytest.raises(ValueError):
