@@ -79,8 +79,44 @@ def run(out_path=None):
             return new
         r["reference_torch_ops_on_gpu_us"] = timed(reference_chain, max(iters // 10, 3), warm=2)
         r["speedup_vs_reference_torch_ops_on_gpu"] = r["reference_torch_ops_on_gpu_us"] / r["plan_step_total_us"]
+        # ---- round 2: the tail of a step (restore + fix-up + SGD) and the head of the next one (save + quantize)
+        # unfused (four launches + torch's multi-tensor SGD) against the fused optimizer step (one launch, 24 B/elt)
+        ref_params = [torch.nn.Parameter(p.clone()) for p in params]
+        opt = torch.optim.SGD(ref_params, lr=1e-3, momentum=0.9, nesterov=True, weight_decay=2.2e-4)
+        ref_plan = QuantizationPlan([p.data for p in ref_params], s, 256)
+        for p, g_ in zip(ref_params, grads):
+            p.grad = g_.clone()
+        ref_plan.save_and_quantize_()
+
+        def unfused_tail():
+            ref_plan.restore_master()
+            ref_plan.backward_([p.grad for p in ref_params], "complicated")
+            opt.step()
+            ref_plan.save_and_quantize_()
+        r["unfused_restore_fixup_sgd_requantize_us"] = timed(unfused_tail, iters)
+        plan.save_and_quantize_()
+        if 256 <= 512:
+            r["fused_sgd_step_us"] = timed(lambda: plan.fused_step_(grads, "complicated", 1e-3, 0.9, 2.2e-4, True), iters)
+            r["fused_sgd_hbm_floor_us_24B_per_elt"] = numel * 24 / 6575.4e9 * 1e6
+        # ---- differentiable-quantization step: CentroidPlan (3 launches for the model) vs the per-tensor ops
+        from quantized_distillation_b200.plan import CentroidPlan
+        src = [p.clone() for p in params]
+        pts = [torch.linspace(0, 1, 4, device=dev) for _ in params]
+        cplan = CentroidPlan(src, [torch.empty_like(t) for t in src], pts, 256)
+        funs = [Q.nonUniformQuantization_variable(bucket_size=256, pre_process_tensors=True, tensor=t) for t in src]
+
+        def per_tensor_centroids():
+            for f_, pt, g_ in zip(funs, pts, grads):
+                f_.forward(None, pt)
+                f_.backward(g_)
+
+        def plan_centroids():
+            cplan.forward_()
+            cplan.backward_(grads)
+        r["centroid_step_per_tensor_ops_us"] = timed(per_tensor_centroids, max(iters // 4, 5))
+        r["centroid_step_plan_us"] = timed(plan_centroids, iters)
         res[name] = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in r.items()}
-        del plan
+        del plan, ref_plan, cplan
     # single big tensor: stock torch chain vs fused kernel (BASELINE config 5 flavour)
     n = 1 << 26
     x = torch.randn(n, device=dev) * 0.05
