@@ -12,8 +12,10 @@ import json
 import subprocess
 import sys
 
-LABELS = {"warp_rows_kernel<2, (int)-1, 2, 1>": "uniform fwd, bucket 256", "warp_rows_kernel<2, 0, 2, 1>": "uniform fwd+bwd STE, bucket 256",
-          "warp_rows_kernel<2, 1, 2, 1>": "uniform fwd+bwd truncated, bucket 256",
+LABELS = {"warp_rows_kernel<2, (int)-1, 2, 1": "uniform fwd, bucket 256", "warp_rows_kernel<2, 0, 2, 1": "uniform fwd+bwd STE, bucket 256",
+          "warp_rows_kernel<2, 1, 2, 1": "uniform fwd+bwd truncated, bucket 256",
+          "warp_rows_kernel<2, 2, 2, 1, 1>": "uniform fwd+bwd min/max, bucket 256 (HEADLINE; r_b summed per element)",
+          "warp_rows_kernel<2, 2, 2, 1, 0>": "uniform bwd min/max alone, bucket 256 (r_b summed in groups)",
           "warp_rows_kernel<2, 2, 2, 1>": "uniform fwd+bwd min/max, bucket 256 (HEADLINE)",
           "warp_rows_kernel<3, 4,": "centroid op K=4 (lane table), bucket 256", "warp_rows_kernel<3, 16,": "centroid op K=16 (lane table), bucket 256",
           "points_grad_partial": "centroid gradient", "grid_stats_partial": "grid path (bucket None): chunk min/max",
@@ -76,7 +78,7 @@ def main(rep, out_md, traffic_json=None):
         for o in out:
             f.write(f"| `{o['name'][:70]}` | {o['what']} | {o['us']:.1f} | {o['rd']:.1f} | {o['wr']:.1f} | {o['dram']:.1f} | {o['inst']:.1f} | "
                     f"{o['issue']:.1f} | {o['occ']:.1f} | {o['regs']} | {o['smem']} | {o['grid']} x {o['block']} | {o['stalls']} |\n")
-            if traffic_json and "warp_rows_kernel<2, 2, 2, 1>" in o["name"]:
+            if traffic_json and ("warp_rows_kernel<2, 2, 2, 1, 1>" in o["name"] or "warp_rows_kernel<2, 2, 2, 1>" in o["name"]) and o["wr"] > 300:
                 json.dump({"uniform_fwd_bwd_minmax_64Mi_dram_bytes": int((o["rd"] + o["wr"]) * 1e6), "algorithmic_bytes": 16 * (1 << 26),
                            "source": f"{out_md} (ncu --set full, one launch of the headline kernel)"}, open(traffic_json, "w"), indent=1)
     print(open(out_md).read())
