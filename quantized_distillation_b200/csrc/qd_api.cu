@@ -2,9 +2,10 @@
 // and the extern "C" entry points declared in include/qd_b200.h.
 //
 // Path selection by row length L (= bucket, or n when bucket is None / n < bucket):
-//     L <= 1024                  warp path   (registers, 1 HBM pass)
-//     L <= QD_MAX_STAGED_BUCKET  block path  (TMA-staged shared memory, 1 HBM pass)
-//     otherwise                  grid path   (two streaming passes)
+//     L <= 1024                  warp path    (registers, 1 HBM pass)
+//     L <= QD_MAX_STAGED_BUCKET  staged path  (TMA chunk ring in shared memory, 1 HBM pass; CTA size by L)
+//     otherwise                  grid path    (two streaming passes)
+// Thresholds inside these ranges come from profiles/block_path_r2_{variants,small_rows}.md.
 #include <cuda_runtime.h>
 
 #include <cstdarg>

@@ -1,25 +1,23 @@
-// qd_block_path.cuh -- rows of 1025 .. QD_MAX_STAGED_BUCKET elements: ONE CTA
-// (or one warp) PER ROW, still one pass over HBM.  Three variants of the same kernel:
+// qd_block_path.cuh -- the round-1 kernels for rows of 1025 .. QD_MAX_STAGED_BUCKET elements, plus the TMA /
+// mbarrier primitives and CTA reductions the staged ring (qd_staged_path.cuh) builds on.
 //
-// WARP TWO-PASS (rows up to kWarpTwoPassMaxRow floats): a warp streams its row once for
-// min/max and again (L1/L2 hit) for the element-wise pass; no block barrier anywhere, sixteen
-// rows in flight per CTA.
+// Since round 2 the deterministic uniform op (forward, every backward mode) and the centroid op run on the
+// staged chunk ring; this kernel keeps the ops the ring does not implement -- per-row statistics, x_hat in the
+// padded layout, stochastic rounding -- in two variants (the benchmark hook can still force them for the
+// other ops, which is how profiles/block_path_r2_variants.md was measured):
 //
-// STAGED (longer rows): the row is staged in shared memory by
-// the TMA bulk-copy engine (cp.async.bulk.shared::cluster.global with mbarrier
-// complete_tx; SASS UBLKCP): one elected thread enqueues the row in 32 KB
-// chunks, each chunk signalling its own mbarrier, and the 512 threads reduce
-// chunk c while chunks c+1.. are still in flight.  Rows whose global address is
-// not 16-byte aligned fall back to a cooperative ld.global -> st.shared copy.
-// Shared memory is sized to the row (dynamic), so several CTAs are resident per
-// SM and the store phase of one row overlaps the load phase of another.
+// WARP TWO-PASS (GROUP = 32, rows up to 2 * kWarpTwoPassMaxRow floats): a warp streams its row once for
+// min/max (tagged L2::evict_last) and again (L2 hit) for the element-wise pass; no block barrier anywhere,
+// sixteen rows in flight per CTA.
 //
-// CTA L2 re-read (fallback, selectable with QD_STAGED_MAX): the CTA streams the row
-// once for min/max and again for the element-wise pass; the second read of a
-// <= 192 KB row is an L2 hit, so HBM still sees one read and one write, and no
-// shared memory is needed, so four CTAs per SM overlap each other's phases.
+// WHOLE-ROW STAGING (GROUP = 512, longer rows): the row is staged in shared memory by the TMA bulk-copy engine
+// (cp.async.bulk.shared::cluster.global with mbarrier complete_tx; SASS UBLKCP): one elected thread enqueues the
+// row in 32 KB chunks, each chunk signalling its own mbarrier, and the 512 threads reduce chunk c while chunks
+// c+1.. are still in flight.  Rows whose global address is not 16-byte aligned fall back to a cooperative
+// ld.global -> st.shared copy.  Shared memory is sized to the row (dynamic).
 //
-// All element loops are 128-bit (LDS.128 / LDG.128 / STG.128) with a scalar tail.
+// The min/max backward here uses the same two-sweep formulation as the ring (analytic extremes of q, the two
+// changed elements patched after the sweep).  All element loops are 128-bit with a scalar tail.
 #pragma once
 #include "qd_rowops.cuh"
 
@@ -91,9 +89,8 @@ __device__ __forceinline__ double cta_sum(double v, double* scratch) {
     return warp_sum(r);  // fixed tree: deterministic
 }
 
-// Measured on B200 (tools/block_bench.py, 64 Mi floats): warp-per-row two-pass wins up to 2048
-// floats per row, the TMA-staged CTA above that, up to the 49152-float shared-memory limit; the
-// CTA-wide L2 re-read variant is kept for completeness (QD_STAGED_MAX can select it).
+// Round-1 measurement (tools/block_bench.py, 64 Mi floats): warp-per-row two-pass won up to 2048-4096 floats per
+// row, the whole-row staging above that, up to the 49152-float shared-memory limit.
 constexpr int kStagedMaxRow = QD_MAX_STAGED_BUCKET;  // floats; longer rows would use the L2 re-read variant
 constexpr int kWarpTwoPassMaxRow = 2048;  // floats; rows up to here: one WARP per row, two passes (second from L1/L2)
 
