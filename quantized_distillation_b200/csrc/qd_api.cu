@@ -343,32 +343,58 @@ extern "C" int qd_scale_down(const float* x, float* xhat, float* alpha, float* b
     return run_rows<OP_SCALE, BWD_OFF>(P, workspace, workspace_bytes, s);
 }
 
-// y*alpha + beta (+ mean): groups of four consecutive elements, one 64-bit division per group when the rows
-// are multiples of four (every bucketed layout of the reference), 128-bit accesses when the pointers allow
+// Tiled helper kernels (inv_scale, pack, unpack): one CTA iteration = one contiguous tile of kTileGroups thread-groups,
+// every thread owns kTileU groups of it, 256 groups apart, and issues all kTileU loads before the first use -- 64 B per
+// thread in flight instead of 16 (Little: 148 SMs x 2048 threads x 16 B = 4.8 MB does not cover 6.5 TB/s x ~1 us).
+constexpr int kTileU = 4;
+constexpr int kTileGroups = 256 * kTileU;
+
+// (row, offset in row) of an element position that advances by fixed steps: one 64-bit division per THREAD, none per group
+struct RowCursor {
+    int64_t row, rem;
+    __device__ __forceinline__ void advance(int64_t d_rows, int64_t d_rem, int64_t L) {
+        row += d_rows;
+        rem += d_rem;
+        if (rem >= L) { rem -= L; ++row; }
+    }
+};
+
+// y*alpha + beta (+ mean): groups of four consecutive elements, 128-bit accesses when the rows are multiples of four
+// (every bucketed layout of the reference) and the pointers allow
 __global__ void __launch_bounds__(256) inv_scale_kernel(const float* __restrict__ y, float* __restrict__ out, const float* __restrict__ alpha,
                                                         const float* __restrict__ beta, const float* __restrict__ mean, Geometry geo) {
     const float m = mean ? *mean : 0.f;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const bool vec = (geo.rows == 1 || geo.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t L = geo.row_len;
+    const bool vec = (geo.rows == 1 || L % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     const int64_t groups = vec ? (geo.n >> 2) : 0;
-    // the row of a group advances by a fixed (rows, remainder) step per iteration: two divisions per THREAD, none per group
-    const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t row = (geo.rows == 1) ? 0 : (g0 * 4) / geo.row_len;
-    int64_t rem = (geo.rows == 1) ? 0 : (g0 * 4) - row * geo.row_len;
-    const int64_t step_rows = (geo.rows == 1) ? 0 : (stride * 4) / geo.row_len;
-    const int64_t step_rem = (geo.rows == 1) ? 0 : (stride * 4) - step_rows * geo.row_len;
-    for (int64_t gi = g0; gi < groups; gi += stride) {
-        const float a = alpha[row], b = beta[row];
-        const float4 t = ld_stream4(y + gi * 4);
-        float4 o = make_float4(from_unit(t.x, a, b), from_unit(t.y, a, b), from_unit(t.z, a, b), from_unit(t.w, a, b));  // mul_, add_ (:142-143)
-        if (mean) { o.x = __fadd_rn(o.x, m); o.y = __fadd_rn(o.y, m); o.z = __fadd_rn(o.z, m); o.w = __fadd_rn(o.w, m); }  // add_(mean) (:148)
-        st_stream4(out + gi * 4, o);
-        row += step_rows;
-        rem += step_rem;
-        if (rem >= geo.row_len) { rem -= geo.row_len; ++row; }
+    const int64_t tiles = (groups + kTileGroups - 1) / kTileGroups;
+    const int64_t e_first = ((int64_t)blockIdx.x * kTileGroups + threadIdx.x) * 4;
+    RowCursor cur{e_first / L, e_first % L};
+    const int64_t du_rows = (256 * 4) / L, du_rem = (256 * 4) % L;
+    const int64_t dt = (int64_t)gridDim.x * kTileGroups * 4;
+    const int64_t dt_rows = dt / L, dt_rem = dt % L;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t g0 = tile * kTileGroups + threadIdx.x;
+        float4 t[kTileU];
+#pragma unroll
+        for (int u = 0; u < kTileU; ++u)
+            if (g0 + u * 256 < groups) t[u] = ld_stream4(y + (g0 + u * 256) * 4);
+        RowCursor c = cur;
+#pragma unroll
+        for (int u = 0; u < kTileU; ++u) {
+            if (g0 + u * 256 < groups) {
+                const float a = alpha[c.row], b = beta[c.row];
+                float4 o = make_float4(from_unit(t[u].x, a, b), from_unit(t[u].y, a, b), from_unit(t[u].z, a, b), from_unit(t[u].w, a, b));  // mul_, add_ (:142-143)
+                if (mean) { o.x = __fadd_rn(o.x, m); o.y = __fadd_rn(o.y, m); o.z = __fadd_rn(o.z, m); o.w = __fadd_rn(o.w, m); }  // add_(mean) (:148)
+                st_stream4(out + (g0 + u * 256) * 4, o);
+            }
+            c.advance(du_rows, du_rem, L);
+        }
+        cur.advance(dt_rows, dt_rem, L);
     }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = groups * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < geo.n; i += stride) {
-        const int64_t row = (geo.rows == 1) ? 0 : i / geo.row_len;
+        const int64_t row = (geo.rows == 1) ? 0 : i / L;
         float v = from_unit(y[i], alpha[row], beta[row]);
         if (mean) v = __fadd_rn(v, m);
         out[i] = v;
@@ -383,7 +409,7 @@ extern "C" int qd_inv_scale_down(const float* y, float* out, const float* alpha,
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    int64_t need = (n / 4 + 255) / 256 + 1;
+    int64_t need = (n / 4 + kTileGroups - 1) / kTileGroups + 1;
     int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
     inv_scale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, out, alpha, beta, mean, g);
     QD_CUDA(cudaGetLastError());
@@ -690,37 +716,61 @@ extern "C" int qd_index_histogram(const uint8_t* idx_u8, int64_t n, int num_bins
 }
 
 // ------------------------------------------------------------------ f2: packed codec
-// one thread = 8 consecutive codes in (one 64-bit load), BITS bytes out (one store of that width); BITS is a
+// one thread-group = 16 consecutive codes in (one 128-bit load), 2*BITS bytes out (one store of that width); BITS is a
 // template parameter so that every shift, mask and access width is a compile-time constant
 template <int BITS>
-__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ idx, uint8_t* __restrict__ packed, int64_t n) {
-    const int64_t groups = (n + 7) / 8;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ uint32_t squeeze4(uint32_t w) {  // four codes in four bytes -> 4*BITS bits
     constexpr unsigned mask = (1u << BITS) - 1u;
+    return (w & mask) | (((w >> 8) & mask) << BITS) | (((w >> 16) & mask) << (2 * BITS)) | (((w >> 24) & mask) << (3 * BITS));
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ idx, uint8_t* __restrict__ packed, int64_t n) {
+    const int64_t groups = (n + 15) / 16;
+    const int64_t full = n / 16;   // groups with all sixteen codes present
+    const int64_t tiles = (groups + kTileGroups - 1) / kTileGroups;
     const int64_t out_bytes = (n * BITS + 7) / 8;
-    const bool in_vec = (reinterpret_cast<uintptr_t>(idx) & 7) == 0;
-    const bool out_vec = (reinterpret_cast<uintptr_t>(packed) & 7) == 0;
-    for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += stride) {
-        const int64_t e0 = gidx * 8;
-        unsigned long long codes = 0;
-        if (in_vec && e0 + 8 <= n) {
-            codes = *reinterpret_cast<const unsigned long long*>(idx + e0);
-        } else {
-            for (int j = 0; j < 8; ++j)
-                if (e0 + j < n) codes |= (unsigned long long)idx[e0 + j] << (8 * j);
-        }
-        unsigned long long word = 0;
+    const bool in_vec = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
+    const bool out_vec = (reinterpret_cast<uintptr_t>(packed) & 15) == 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t g0 = tile * kTileGroups + threadIdx.x;
+        uint4 c[kTileU];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) word |= (unsigned long long)((unsigned)(codes >> (8 * j)) & mask) << (j * BITS);
-        uint8_t* dst = packed + gidx * BITS;
-        if (out_vec && (gidx + 1) * BITS <= out_bytes) {
-            if constexpr (BITS == 8) *reinterpret_cast<unsigned long long*>(dst) = word;
-            else if constexpr (BITS == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)word;
-            else if constexpr (BITS == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word;
-            else *dst = (uint8_t)word;
-        } else {
-            for (int b = 0; b < BITS; ++b)
-                if (gidx * BITS + b < out_bytes) dst[b] = (uint8_t)(word >> (8 * b));
+        for (int u = 0; u < kTileU; ++u) {
+            const int64_t g = g0 + u * 256;
+            if (in_vec && g < full) {
+                c[u] = __ldcs(reinterpret_cast<const uint4*>(idx) + g);
+            } else {
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                if (g < groups)
+                    for (int j = 0; j < 16; ++j)
+                        if (g * 16 + j < n) w[j >> 2] |= (uint32_t)idx[g * 16 + j] << (8 * (j & 3));
+                c[u] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kTileU; ++u) {
+            const int64_t g = g0 + u * 256;
+            if (g >= groups) continue;
+            // 16*BITS output bits, low codes first, as two 64-bit halves (the second one is only used for BITS = 8)
+            unsigned long long lo, hi = 0;
+            if constexpr (BITS == 8) {
+                lo = (unsigned long long)c[u].x | ((unsigned long long)c[u].y << 32);
+                hi = (unsigned long long)c[u].z | ((unsigned long long)c[u].w << 32);
+            } else {
+                lo = (unsigned long long)squeeze4<BITS>(c[u].x) | ((unsigned long long)squeeze4<BITS>(c[u].y) << (4 * BITS)) |
+                     ((unsigned long long)squeeze4<BITS>(c[u].z) << (8 * BITS)) | ((unsigned long long)squeeze4<BITS>(c[u].w) << (12 * BITS));
+            }
+            uint8_t* dst = packed + g * (2 * BITS);
+            if (out_vec && g < full) {
+                if constexpr (BITS == 8) __stcs(reinterpret_cast<uint4*>(dst), make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)));
+                else if constexpr (BITS == 4) __stcs(reinterpret_cast<unsigned long long*>(dst), lo);
+                else if constexpr (BITS == 2) __stcs(reinterpret_cast<uint32_t*>(dst), (uint32_t)lo);
+                else __stcs(reinterpret_cast<uint16_t*>(dst), (uint16_t)lo);
+            } else {
+                for (int b = 0; b < 2 * BITS; ++b)
+                    if (g * (2 * BITS) + b < out_bytes) dst[b] = (uint8_t)((b < 8 ? lo >> (8 * b) : hi >> (8 * (b - 8))));
+            }
         }
     }
 }
@@ -731,7 +781,7 @@ extern "C" int qd_pack_indices(const uint8_t* idx_u8, uint8_t* packed, int64_t n
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    int64_t need = ((n + 7) / 8 + 255) / 256;
+    int64_t need = ((n + 15) / 16 + kTileGroups - 1) / kTileGroups;
     int grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (bits == 8) pack_kernel<8><<<grid, 256, 0, s>>>(idx_u8, packed, n);
@@ -742,66 +792,119 @@ extern "C" int qd_pack_indices(const uint8_t* idx_u8, uint8_t* packed, int64_t n
     return QD_OK;
 }
 
-// one thread = FOUR consecutive elements: their codes are one aligned load of 4*BITS bits (a nibble for BITS = 1),
-// the four dequantized values leave as one 128-bit store (a warp writes 512 contiguous bytes); the row of a group
-// advances by a fixed step per iteration (no division per element)
+// one thread-group = FOUR consecutive elements: their codes are one aligned load of 4*BITS bits (a nibble for BITS = 1),
+// the four dequantized values leave as one 128-bit store (a warp writes 512 contiguous bytes).  The unit value of a
+// code comes from a 256-entry table in shared memory: c/S for the uniform scheme (the reference's division, done once
+// per code instead of once per element), the centroid for the non-uniform one.
+template <int BITS>
+__device__ __forceinline__ uint32_t load_codes4(const uint8_t* __restrict__ packed, int64_t e0, int64_t in_bytes, bool ivec) {
+    if constexpr (BITS == 8) {
+        if (ivec && e0 + 4 <= in_bytes) return __ldcs(reinterpret_cast<const uint32_t*>(packed + e0));
+        uint32_t word = 0;
+        for (int b = 0; b < 4; ++b)
+            if (e0 + b < in_bytes) word |= (uint32_t)packed[e0 + b] << (8 * b);
+        return word;
+    } else if constexpr (BITS == 4) {
+        const int64_t b0 = e0 >> 1;
+        if (ivec && b0 + 2 <= in_bytes) return __ldcs(reinterpret_cast<const uint16_t*>(packed + b0));
+        uint32_t word = packed[b0];
+        if (b0 + 1 < in_bytes) word |= (uint32_t)packed[b0 + 1] << 8;
+        return word;
+    } else if constexpr (BITS == 2) {
+        return packed[e0 >> 2];
+    } else {
+        return (uint32_t)packed[e0 >> 3] >> (unsigned)(e0 & 4);
+    }
+}
+
+// codes of group g (four elements) when the packed pointer is 4-byte aligned and the group is complete
+template <int BITS>
+__device__ __forceinline__ uint32_t load_codes4_fast(const uint8_t* __restrict__ packed, int64_t g) {
+    if constexpr (BITS == 8) return __ldcs(reinterpret_cast<const uint32_t*>(packed) + g);
+    else if constexpr (BITS == 4) return __ldcs(reinterpret_cast<const uint16_t*>(packed) + g);
+    else if constexpr (BITS == 2) return __ldcs(packed + g);
+    else return (uint32_t)__ldcs(packed + (g >> 1)) >> (unsigned)((g & 1) * 4);
+}
+
 template <bool UNIFORM, int BITS>
-__global__ void __launch_bounds__(256) unpack_dequant_kernel(const uint8_t* __restrict__ packed,
+__global__ void __launch_bounds__(256, 4) unpack_dequant_kernel(const uint8_t* __restrict__ packed,
                                                             const float* __restrict__ points, int K,
                                                             const float* __restrict__ alpha, const float* __restrict__ beta,
-                                                            float* __restrict__ q, Geometry geo, float S, float rS) {
-    __shared__ float s_pts[256];
-    if (!UNIFORM) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pts[i] = (i < K) ? points[i] : 0.f;
-        __syncthreads();
+                                                            float* __restrict__ q, Geometry geo, float S) {
+    __shared__ float s_unit[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        if (UNIFORM) s_unit[i] = ((float)i <= S) ? level_to_unit((float)i, S) : 0.f;
+        else s_unit[i] = (i < K) ? points[i] : 0.f;
     }
+    __syncthreads();
+    const int64_t L = geo.row_len;
     const int64_t groups = (geo.n + 3) / 4;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     constexpr unsigned mask = (1u << BITS) - 1u;
-    const int64_t in_bytes = (geo.n * BITS + 7) / 8;
-    const bool ovec = (reinterpret_cast<uintptr_t>(q) & 15) == 0;
-    const bool ivec = (reinterpret_cast<uintptr_t>(packed) & 3) == 0;
-    const bool same_row = geo.rows == 1 || geo.row_len % 4 == 0;   // the four elements of a group share their row
-    const bool small_s = S <= 255.0f;
-    const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t row = (geo.rows == 1) ? 0 : (g0 * 4) / geo.row_len;
-    int64_t rem = (geo.rows == 1) ? 0 : (g0 * 4) - row * geo.row_len;
-    const int64_t step_rows = (geo.rows == 1) ? 0 : (stride * 4) / geo.row_len;
-    const int64_t step_rem = (geo.rows == 1) ? 0 : (stride * 4) - step_rows * geo.row_len;
-    for (int64_t gidx = g0; gidx < groups; gidx += stride) {
-        const int64_t e0 = gidx * 4;
-        uint32_t word;
-        if constexpr (BITS == 8) {
-            const int64_t b0 = e0;
-            if (ivec && b0 + 4 <= in_bytes) word = *reinterpret_cast<const uint32_t*>(packed + b0);
-            else { word = 0; for (int b = 0; b < 4; ++b) if (b0 + b < in_bytes) word |= (uint32_t)packed[b0 + b] << (8 * b); }
-        } else if constexpr (BITS == 4) {
-            const int64_t b0 = e0 >> 1;
-            if (ivec && b0 + 2 <= in_bytes) word = *reinterpret_cast<const uint16_t*>(packed + b0);
-            else { word = packed[b0]; if (b0 + 1 < in_bytes) word |= (uint32_t)packed[b0 + 1] << 8; }
-        } else if constexpr (BITS == 2) {
-            word = packed[e0 >> 2];
-        } else {
-            word = (uint32_t)packed[e0 >> 3] >> (unsigned)(e0 & 4);
-        }
-        float o[4];
+    const bool single = geo.rows == 1;
+    // fast tiles: complete tiles of kTileGroups groups, aligned pointers, the four elements of a group in one row, and
+    // a row cursor that fits 32 bits (rows x row length beyond that only exist for buckets of < 32 floats on > 8 G
+    // elements; they take the general loop below)
+    const bool fast_ok = ((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ((reinterpret_cast<uintptr_t>(packed) & 3) == 0) &&
+                         (single || (L % 4 == 0 && L < (1ll << 30) && geo.rows < (1ll << 31)));
+    const int64_t full_tiles = fast_ok ? geo.n / (kTileGroups * 4) : 0;
+    if (full_tiles > (int64_t)blockIdx.x) {
+        const uint32_t L32 = single ? 1u : (uint32_t)L;
+        const int64_t e_first = ((int64_t)blockIdx.x * kTileGroups + threadIdx.x) * 4;
+        int row = single ? 0 : (int)(e_first / L);
+        uint32_t rem = single ? 0u : (uint32_t)(e_first % L);
+        const int du_rows = single ? 0 : (int)((256 * 4) / L);
+        const uint32_t du_rem = single ? 0u : (uint32_t)((256 * 4) % L);
+        const int64_t dt = (int64_t)gridDim.x * kTileGroups * 4;
+        const int dt_rows = single ? 0 : (int)(dt / L);
+        const uint32_t dt_rem = single ? 0u : (uint32_t)(dt % L);
+        // Everything a tile READS (codes, alpha, beta of its kTileU groups) is fetched one tile ahead: the stores of a
+        // tile are asm volatile (no load moves across them), and under a store-dominated stream a read round trip is
+        // several microseconds -- without the prefetch every group of four stores waited for its own alpha/beta read.
+        struct Fetched { uint32_t w[kTileU]; float a[kTileU], b[kTileU]; };
+        auto fetch = [&](int64_t tile, int r, uint32_t m, Fetched& f) {
+            const int64_t g0 = tile * kTileGroups + threadIdx.x;
 #pragma unroll
+            for (int u = 0; u < kTileU; ++u) f.w[u] = load_codes4_fast<BITS>(packed, g0 + u * 256);
+#pragma unroll
+            for (int u = 0; u < kTileU; ++u) {
+                f.a[u] = __ldg(alpha + r);
+                f.b[u] = __ldg(beta + r);
+                r += du_rows;
+                m += du_rem;
+                if (m >= L32) { m -= L32; ++r; }
+            }
+        };
+        Fetched cur;
+        fetch(blockIdx.x, row, rem, cur);
+        for (int64_t tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
+            Fetched nxt = cur;
+            row += dt_rows;
+            rem += dt_rem;
+            if (rem >= L32) { rem -= L32; ++row; }
+            if (tile + gridDim.x < full_tiles) fetch(tile + gridDim.x, row, rem, nxt);
+            float* dst = q + (tile * kTileGroups + threadIdx.x) * 4;
+#pragma unroll
+            for (int u = 0; u < kTileU; ++u) {
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = from_unit(s_unit[(cur.w[u] >> (j * BITS)) & mask], cur.a[u], cur.b[u]);
+                st_stream4(dst + u * 1024, make_float4(o[0], o[1], o[2], o[3]));
+            }
+            cur = nxt;
+        }
+    }
+    // general loop: the last partial tile, unaligned pointers, ragged buckets
+    const int64_t in_bytes = (geo.n * BITS + 7) / 8;
+    const bool ivec = (reinterpret_cast<uintptr_t>(packed) & 3) == 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = full_tiles * kTileGroups + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const int64_t e0 = g * 4;
+        const uint32_t w = load_codes4<BITS>(packed, e0, in_bytes, ivec);
         for (int j = 0; j < 4; ++j) {
-            const unsigned c = (word >> (j * BITS)) & mask;
-            int64_t r = row;
-            if (!same_row) r = (e0 + j < geo.n) ? (e0 + j) / geo.row_len : row;
-            const float unit = UNIFORM ? (small_s ? small_level_to_unit((float)c, S, rS) : level_to_unit((float)c, S)) : s_pts[c];
-            o[j] = from_unit(unit, alpha[r], beta[r]);
+            if (e0 + j >= geo.n) break;
+            const int64_t r = single ? 0 : (e0 + j) / L;
+            q[e0 + j] = from_unit(s_unit[(w >> (j * BITS)) & mask], alpha[r], beta[r]);
         }
-        if (ovec && e0 + 4 <= geo.n) {
-            st_stream4(q + e0, make_float4(o[0], o[1], o[2], o[3]));
-        } else {
-            for (int j = 0; j < 4; ++j)
-                if (e0 + j < geo.n) q[e0 + j] = o[j];
-        }
-        row += step_rows;
-        rem += step_rem;
-        if (rem >= geo.row_len) { rem -= geo.row_len; ++row; }
     }
 }
 
@@ -813,8 +916,8 @@ static int unpack_common(const uint8_t* packed, int bits, const float* alpha, co
     DevInfo* di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    int64_t need = ((n + 3) / 4 + 255) / 256;
-    *grid = (int)(need < (int64_t)di->sms * 8 ? need : (int64_t)di->sms * 8);
+    int64_t need = ((n + 3) / 4 + kTileGroups - 1) / kTileGroups;
+    *grid = (int)(need < (int64_t)di->sms * 4 ? need : (int64_t)di->sms * 4);   // one resident wave (__launch_bounds__(256, 4))
     return QD_OK;
 }
 
@@ -827,10 +930,10 @@ extern "C" int qd_unpack_dequant_uniform(const uint8_t* packed, int bits, const 
     if (rc) return rc;
     const float S = (float)(levels - 1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (bits == 8) unpack_dequant_kernel<true, 8><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
-    else if (bits == 4) unpack_dequant_kernel<true, 4><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
-    else if (bits == 2) unpack_dequant_kernel<true, 2><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
-    else unpack_dequant_kernel<true, 1><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S, 1.0f / S);
+    if (bits == 8) unpack_dequant_kernel<true, 8><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S);
+    else if (bits == 4) unpack_dequant_kernel<true, 4><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S);
+    else if (bits == 2) unpack_dequant_kernel<true, 2><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S);
+    else unpack_dequant_kernel<true, 1><<<grid, 256, 0, st>>>(packed, nullptr, 0, alpha, beta, q, geo, S);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
@@ -844,10 +947,10 @@ extern "C" int qd_unpack_dequant_nonuniform(const uint8_t* packed, int bits, con
     int rc = unpack_common(packed, bits, alpha, beta, q, n, bucket, &geo, &grid);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (bits == 8) unpack_dequant_kernel<false, 8><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
-    else if (bits == 4) unpack_dequant_kernel<false, 4><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
-    else if (bits == 2) unpack_dequant_kernel<false, 2><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
-    else unpack_dequant_kernel<false, 1><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f, 0.f);
+    if (bits == 8) unpack_dequant_kernel<false, 8><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f);
+    else if (bits == 4) unpack_dequant_kernel<false, 4><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f);
+    else if (bits == 2) unpack_dequant_kernel<false, 2><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f);
+    else unpack_dequant_kernel<false, 1><<<grid, 256, 0, st>>>(packed, points, num_points, alpha, beta, q, geo, 0.f);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }

@@ -871,6 +871,60 @@ def test_packed_codec_round_trip(Q):
     assert codec.get_size_reduction(4, None) == 8
 
 
+def test_packed_codec_many_tiles_and_unaligned_views(Q):
+    """The tiled pack / unpack / inv_scale kernels past one tile per CTA (the row cursor advances by tile steps),
+    with ragged buckets, and on views whose pointers are not 16-byte aligned (byte-wise fallbacks)."""
+    from quantized_distillation_b200 import _native as N
+    from quantized_distillation_b200 import codec
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 40_000_003
+    x = torch.randn(n, generator=g, device="cuda") * 0.05
+    for s, bucket in ((16, 256), (4, 100), (256, 1000), (2, None)):
+        pt = codec.encode_uniform(x, s, bucket)
+        q, sf = Q.uniformQuantization(x, s, bucket_size=bucket)
+        assert torch.equal(codec.decode(pt), q), (s, bucket)
+        # inv_scale(scale(x)) against the two stock-torch ops of the reference (mul_, add_: no FMA)
+        f = Q.ScalingFunction("linear", False, False, bucket, False)
+        y = f.scale_down(x)
+        back = f.inv_scale_down(y)
+        if bucket is None:
+            want = y * f.alpha + f.beta
+        else:
+            rows = -(-n // bucket)
+            yp = torch.zeros(rows * bucket, device="cuda")
+            yp[:n] = y.view(-1)[:n]
+            want = (yp.view(rows, bucket) * f.alpha.view(-1, 1) + f.beta.view(-1, 1)).view(-1)[:n]
+        assert torch.equal(back.view(-1), want.view(-1)), (s, bucket)
+    # unaligned device pointers straight through the C ABI
+    lib, sp = N.lib(), N.stream_ptr()
+    m = 100_001
+    idx_store = torch.randint(0, 16, (m + 3,), dtype=torch.uint8, device="cuda", generator=g)
+    for off in (0, 1, 3):
+        for bits in (1, 2, 4, 8):
+            codes = (idx_store & ((1 << bits) - 1))[off:off + m]          # a view: pointer offset by `off` bytes
+            out_store = torch.zeros((m * bits + 7) // 8 + 3, dtype=torch.uint8, device="cuda")
+            packed = out_store[off:off + (m * bits + 7) // 8]
+            N.check(lib.qd_pack_indices(N.ptr(codes), N.ptr(packed), m, bits, sp))
+            c = codes.cpu().numpy().astype(np.uint64)
+            per = 8 // bits
+            pad = np.zeros(-(-m // per) * per, dtype=np.uint64)
+            pad[:m] = c
+            want = np.zeros(len(pad) // per, dtype=np.uint64)
+            for j in range(per):
+                want |= pad[j::per] << np.uint64(j * bits)
+            assert np.array_equal(packed.cpu().numpy(), want.astype(np.uint8)), (off, bits)
+            # unpack from the unaligned view into an unaligned float view
+            alpha = torch.full((1,), 2.0, device="cuda")
+            beta = torch.full((1,), -1.0, device="cuda")
+            q_store = torch.zeros(m + 3, device="cuda")
+            qv = q_store[off:off + m]
+            levels = 1 << bits
+            N.check(lib.qd_unpack_dequant_uniform(N.ptr(packed), bits, N.ptr(alpha), N.ptr(beta), N.ptr(qv), m, 0, levels, sp))
+            # a tensor divisor: torch's CUDA division by a Python scalar multiplies by the reciprocal instead
+            wantq = (codes.float() / torch.full((m,), float(levels - 1), device="cuda")) * 2.0 + (-1.0)
+            assert torch.equal(qv, wantq), (off, bits)
+
+
 def test_size_accounting_matches_reference_formula(Q):
     from quantized_distillation_b200 import codec
     torch.manual_seed(0)

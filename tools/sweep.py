@@ -19,7 +19,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def run(dev=None, out_path=None, max_log2=28, min_log2=10):
+def run(dev=None, out_path=None, max_log2=28, min_log2=10, only=None):
     import torch
     from quantized_distillation_b200 import _native as N
     dev = dev or torch.device("cuda", torch.cuda.current_device())
@@ -101,6 +101,13 @@ def run(dev=None, out_path=None, max_log2=28, min_log2=10):
                 ops["pack_4bit"] = (1.5, lambda i: N.check(lib.qd_pack_indices(N.ptr(idx[i]), N.ptr(packed), n, 4, sp)))
                 ops["unpack_dequant_uniform_4bit"] = (4.5, lambda i: N.check(lib.qd_unpack_dequant_uniform(
                     N.ptr(packed), 4, N.ptr(alpha), N.ptr(beta), N.ptr(qs[i]), n, bucket, 16, sp)))
+                # write-only yardstick (torch's fill kernel, not ours): what a pure store stream reaches on this part
+                ops["yardstick_fill_torch"] = (4, lambda i: qs[i].fill_(1.0))
+                ops["yardstick_copy_torch"] = (8, lambda i: qs[i].copy_(xs[i]))
+                packed2 = torch.empty((n * 2 + 7) // 8, dtype=torch.uint8, device=dev)
+                ops["pack_2bit"] = (1.25, lambda i: N.check(lib.qd_pack_indices(N.ptr(idx[i]), N.ptr(packed2), n, 2, sp)))
+                ops["unpack_dequant_nonuniform_4bit"] = (4.5, lambda i: N.check(lib.qd_unpack_dequant_nonuniform(
+                    N.ptr(packed), 4, N.ptr(pts16), 16, N.ptr(alpha), N.ptr(beta), N.ptr(qs[i]), n, bucket, sp)))
                 ops["uniform_fwd_bwd_minmax"] = (16, lambda i: N.check(lib.qd_uniform_fwd_bwd(
                     N.ptr(xs[i]), N.ptr(gs[i]), N.ptr(qs[i]), N.ptr(gos[i]), n, bucket, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(), sp)))
                 ops["uniform_bwd_minmax"] = (12, lambda i: N.check(lib.qd_uniform_bwd(
@@ -108,6 +115,8 @@ def run(dev=None, out_path=None, max_log2=28, min_log2=10):
             for i in range(nbuf):
                 idx[i].random_(0, 4)
             for name, (bpe, fn) in ops.items():
+                if only and not any(k in name for k in only):
+                    continue
                 sec = timeit(fn, nbuf, iters)
                 gbs = n * bpe / sec / 1e9
                 rows.append({"op": name, "n": n, "bucket": bucket or None, "us": round(sec * 1e6, 2), "bytes_per_elem": bpe,
@@ -132,5 +141,6 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=None)
     ap.add_argument("--max-log2", type=int, default=28)
     ap.add_argument("--min-log2", type=int, default=10)
+    ap.add_argument("--only", default="", help="comma-separated substrings: time only the ops whose name contains one of them")
     a = ap.parse_args()
-    print(run(out_path=a.out, max_log2=a.max_log2, min_log2=a.min_log2))
+    print(run(out_path=a.out, max_log2=a.max_log2, min_log2=a.min_log2, only=[k for k in a.only.split(",") if k]))
