@@ -596,6 +596,36 @@ def main():
     assert torch.equal(hq, q.cpu()), "e2e result differs from the resident-HBM result"
     e2e_gbs = N_ELEMS * BYTES_PER_ELEM / e2e_s / 1e9 * world
 
+    # ---- the ceiling of the e2e leg on this box: the same four pinned buffers moved by plain cudaMemcpyAsync, both
+    # directions at once, no kernel, every rank at the same time (so that at N > 1 it shows what the host side --
+    # DRAM, PCIe switches -- gives N concurrent ranks); counted in the e2e leg's unit (16 algorithmic bytes per element)
+    dx, dg = torch.empty_like(x), torch.empty_like(x)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_step():
+        with torch.cuda.stream(s_in):
+            dx.copy_(hx, non_blocking=True)
+            dg.copy_(hg, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hq.copy_(q, non_blocking=True)
+            hgo.copy_(gout, non_blocking=True)
+
+    copy_step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        copy_step()
+    torch.cuda.synchronize(dev)
+    copy_s = (time.perf_counter() - t0) / 4
+    if world > 1:
+        t = torch.tensor([copy_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_s = float(t.item())
+    copy_gbs = N_ELEMS * BYTES_PER_ELEM / copy_s / 1e9 * world
+    del dx, dg
+
     peak, peak_src = load_peaks()
     out = {
         "metric": "fake_quant_fused_fwd_bwd_algorithmic_GBps", "value": round(value, 1), "unit": "GB/s",
@@ -605,7 +635,10 @@ def main():
         "clocks": clocks,
         "e2e": {"value": round(e2e_gbs, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * N_ELEMS * 4 * world,
                 "d2h_bytes_per_step": 2 * N_ELEMS * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps,
-                "api": "qd_uniform_fwd_bwd_host (pinned host tensors in and out)", "pinned_buffers_numa": numa.applied},
+                "api": "qd_uniform_fwd_bwd_host (pinned host tensors in and out)", "pinned_buffers_numa": numa.applied,
+                "copy_ceiling": {"value": round(copy_gbs, 2), "unit": "GB/s", "frac": round(e2e_gbs / copy_gbs, 4),
+                                 "what": "the same pinned buffers moved by plain cudaMemcpyAsync, both directions at once, "
+                                         "no kernel, all ranks concurrently, in the e2e leg's unit"}},
         "gpu_launches": steps,
         "roofline": {"bound": "hbm", "achieved": round(per_gpu_gbs, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(per_gpu_gbs / peak, 4), "frac_of_nominal_8000": round(per_gpu_gbs / 8000.0, 4),

@@ -225,7 +225,9 @@ int qd_multi_l2norm(const float* const* tensors, const int64_t* n, int count, fl
 /* ---- host-buffer entry points (what a CPU-tensor caller gets) ------------
  * Inputs and outputs in HOST memory (pinned for full PCIe rate); the call
  * pipelines H2D, the fused kernel and D2H in row-aligned chunks on internal
- * streams of `device` and returns when the outputs are complete. */
+ * streams of `device` -- or, for pinned tensors of at most 8 Mi elements, runs
+ * one launch straight on the (device-addressable) host pointers -- and returns
+ * when the outputs are complete.  Pageable memory is accepted (slower copies). */
 int qd_uniform_fwd_host(const float* x_host, float* q_host, int64_t n, int64_t bucket, int levels, int device);
 int qd_uniform_fwd_bwd_host(const float* x_host, const float* g_host, float* q_host, float* gout_host,
                             int64_t n, int64_t bucket, int levels, int mode, int device);
@@ -236,7 +238,10 @@ int qd_uniform_fwd_bwd_host(const float* x_host, const float* g_host, float* q_h
  *   key 1: longest row (floats) that keeps two rows in flight per CTA in the staged path
  *   key 2: threads per CTA of the staged path (64 / 128 / 256 / 512 / 1024)
  *   key 3: warp-path min/max backward sums r_b per element in float64 (1) or in float32 groups of four (0);
- *          built-in choice: per element when q is written in the same pass, grouped for the backward alone */
+ *          built-in choice: per element when q is written in the same pass, grouped for the backward alone
+ *   key 4: longest row (floats) taken by the warp path (<= 1024)
+ *   key 5 / 6 / 7: host entry points: pipeline slots (1..8) / chunk elements / staging path (0 = chunked copies,
+ *          1 = one launch on pinned host pointers) */
 int qd_debug_set_tuning(int key, int64_t value);
 
 /* ---- self tests used by tests/ (device side arithmetic checks) ---------- */

@@ -140,6 +140,7 @@ extern "C" int qd_debug_set_tuning(int key, int64_t value) {
     g_tune[key] = value;
     return QD_OK;
 }
+extern "C" int64_t qd_internal_tuning(int key) { return (key >= 0 && key < 8) ? g_tune[key] : -1; }   // read by qd_host.cu
 
 // ------------------------------------------------------------------ launchers
 template <int OP, int BWD, int R, bool VEC>

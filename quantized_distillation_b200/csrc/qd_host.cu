@@ -15,6 +15,8 @@
 
 // message of the calling thread (qd_last_error), defined in qd_api.cu
 extern "C" int qd_internal_fail(int code, const char* fmt, ...);
+// measurement hook (qd_debug_set_tuning): key 5 = slots, key 6 = chunk elements, key 7 = staging path (see run_host)
+extern "C" int64_t qd_internal_tuning(int key);
 
 #define QDH_CUDA(call)                                                                                   \
     do {                                                                                                 \
@@ -24,11 +26,13 @@ extern "C" int qd_internal_fail(int code, const char* fmt, ...);
 
 namespace {
 
-// pipeline depth and chunk size: three slots of 16 MiB per buffer sit on the plateau of the tuning
-// sweep of round 1 (tools/e2e_tune.py: ~44 GB/s per PCIe direction from 2 slots x 4 MiB upwards)
+// pipeline depth and chunk size: three slots of 8-16 MiB per buffer sit on the plateau of the tuning
+// sweeps (tools/e2e_variants.py: ~44 GB/s per PCIe direction; slots beyond 2 and chunks beyond 16 MiB change nothing)
 constexpr int kMaxSlots = 8;
 constexpr int kSlots = 3;
 constexpr int64_t kChunkElems = 4 << 20;
+constexpr int64_t kMaxChunkElems = 32 << 20;
+constexpr int64_t kDirectMaxElems = 8 << 20;   // largest tensor run as ONE launch on pinned host pointers
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -38,7 +42,8 @@ struct Slot {
 };
 
 struct HostCtx {
-    bool ready = false;
+    int slots = 0;              // allocated slots
+    int64_t chunk_cap = 0;      // their capacity in elements
     Slot slot[kMaxSlots];
     float *big_x = nullptr, *big_g = nullptr, *big_q = nullptr, *big_gout = nullptr;  // bucket=None path
     int64_t big_cap = 0;
@@ -55,21 +60,30 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-int ensure_ctx(int device, HostCtx** out) {
+int ensure_ctx(int device, int slots, int64_t chunk_elems, HostCtx** out) {
     HostCtx& c = g_ctx[device];
-    if (!c.ready) {
-        for (int i = 0; i < kSlots; ++i) {
+    if (c.slots < slots || c.chunk_cap < chunk_elems) {
+        for (int i = 0; i < c.slots; ++i) {
             Slot& s = c.slot[i];
-            QDH_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-            const size_t bytes = (size_t)kChunkElems * sizeof(float);
+            cudaFree(s.x); cudaFree(s.g); cudaFree(s.q); cudaFree(s.gout); cudaFree(s.ws);
+            s.x = s.g = s.q = s.gout = nullptr;
+            s.ws = nullptr;
+        }
+        c.slots = 0;
+        c.chunk_cap = 0;
+        for (int i = 0; i < slots; ++i) {
+            Slot& s = c.slot[i];
+            if (s.stream == nullptr) QDH_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            const size_t bytes = (size_t)chunk_elems * sizeof(float);
             QDH_CUDA(cudaMalloc(&s.x, bytes));
             QDH_CUDA(cudaMalloc(&s.g, bytes));
             QDH_CUDA(cudaMalloc(&s.q, bytes));
             QDH_CUDA(cudaMalloc(&s.gout, bytes));
-            s.ws_bytes = qd_workspace_bytes(kChunkElems, 0);
+            s.ws_bytes = qd_workspace_bytes(chunk_elems, 0);
             QDH_CUDA(cudaMalloc(&s.ws, s.ws_bytes));
         }
-        c.ready = true;
+        c.slots = slots;
+        c.chunk_cap = chunk_elems;
     }
     *out = &c;
     return QD_OK;
@@ -86,15 +100,41 @@ int run_host(const float* hx, const float* hg, float* hq, float* hgout, int64_t 
     QDH_CUDA(cudaGetDevice(&guard.prev));
     QDH_CUDA(cudaSetDevice(device));
     std::lock_guard<std::mutex> lk(g_mu[device]);
+    const int64_t t_slots = qd_internal_tuning(5), t_chunk = qd_internal_tuning(6), t_path = qd_internal_tuning(7);
+    const int n_slots = (t_slots >= 1 && t_slots <= kMaxSlots) ? (int)t_slots : kSlots;
+    // Pinned (cudaHostAlloc'd / registered) host buffers are device-addressable under UVA: the kernel can read its
+    // inputs and write its outputs straight over PCIe.  One such launch moves ~40 GB/s each way (the staged pipeline:
+    // ~44 of the 49 GB/s two plain copies reach together) but has no pipeline to fill and drain, so it wins up to
+    // ~8 Mi elements (tools/e2e_variants.py: 53.8 vs 49.4 GB/s at 1 Mi, 69.4 vs 65.6 at 4 Mi, 77.4 vs 80.2 at 16 Mi,
+    // 80.0 vs 88.5 at 64 Mi; mixed forms -- DMA one way, the kernel the other -- lose at every size).
+    // key 7: 0 = staged pipeline, 1 = one launch on the host pointers, -1 = this rule.
+    auto device_view = [](const void* p) -> void* {
+        if (p == nullptr) return nullptr;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    };
+    bool direct = t_path >= 0 ? t_path == 1 : n <= kDirectMaxElems;
+    const float *dev_x = nullptr, *dev_g = nullptr;
+    float *dev_q = nullptr, *dev_gout = nullptr;
+    if (direct) {
+        dev_x = static_cast<const float*>(device_view(hx));
+        dev_g = static_cast<const float*>(device_view(hg));
+        dev_q = static_cast<float*>(device_view(hq));
+        dev_gout = static_cast<float*>(device_view(hgout));
+        direct = dev_x != nullptr && dev_q != nullptr && (!bwd || (dev_g != nullptr && dev_gout != nullptr));
+    }
+    // staged pipeline: ~8 chunks per tensor, 8 MiB (below that per-copy overhead wins) to 16 MiB per buffer
+    const int64_t chunk_elems = (t_chunk >= 1024 && t_chunk <= kMaxChunkElems) ? t_chunk : (n >= (32ll << 20) ? kChunkElems : kChunkElems / 2);
     HostCtx* c;
-    int rc = ensure_ctx(device, &c);
+    int rc = ensure_ctx(device, n_slots, chunk_elems, &c);
     if (rc) return rc;
 
     int64_t rows, row_len, padded;
     rc = qd_bucket_geometry(n, bucket, &rows, &row_len, &padded);
     if (rc) return rc;
 
-    if (row_len > kChunkElems) {
+    if (row_len > chunk_elems) {
         // one row spans more than a chunk (bucket None on a large tensor): no row-aligned
         // cut exists, so stage the whole tensor; copies still run at PCIe rate.
         if (c->big_cap < n) {
@@ -129,11 +169,25 @@ int run_host(const float* hx, const float* hg, float* hq, float* hgout, int64_t 
     // row-aligned chunks; the kernel sees each chunk as an independent tensor with the
     // same bucket size, which is exact because rows never straddle a chunk boundary and
     // only the last chunk holds the (short) tail row.
-    const int64_t rows_per_chunk = kChunkElems / row_len;
+    // (A ramp of smaller chunks at the head and the tail to shorten the half-duplex fill / drain was measured and
+    // dropped: copies below 16 MiB lose more to per-copy overhead than the ramp saves, tools/e2e_variants.py.)
+    // the register / staged-row kernels read and write every element once; the grid path (rows beyond
+    // QD_MAX_STAGED_BUCKET floats) makes several passes and keeps its staging
+    if (direct && row_len <= QD_MAX_STAGED_BUCKET) {
+        Slot& s = c->slot[0];
+        rc = bwd ? qd_uniform_fwd_bwd(dev_x, dev_g, dev_q, dev_gout, n, bucket, levels, mode, s.ws, s.ws_bytes, s.stream)
+                 : qd_uniform_fwd(dev_x, dev_q, nullptr, nullptr, nullptr, nullptr, nullptr, n, bucket, levels, nullptr, 0.f, 0,
+                                  0, 0, s.ws, s.ws_bytes, s.stream);
+        if (rc) return rc;
+        QDH_CUDA(cudaStreamSynchronize(s.stream));
+        QDH_CUDA(cudaGetLastError());
+        return QD_OK;
+    }
+    const int64_t rows_per_chunk = chunk_elems / row_len;
     const int64_t chunk = rows_per_chunk * row_len;
     int k = 0;
     for (int64_t off = 0; off < n; off += chunk, ++k) {
-        Slot& s = c->slot[k % kSlots];
+        Slot& s = c->slot[k % n_slots];
         const int64_t len = (n - off < chunk) ? (n - off) : chunk;
         const size_t bytes = (size_t)len * sizeof(float);
         // a chunk shorter than the bucket must still be bucketed like the tail of the
@@ -148,7 +202,7 @@ int run_host(const float* hx, const float* hg, float* hq, float* hgout, int64_t 
         QDH_CUDA(cudaMemcpyAsync(hq + off, s.q, bytes, cudaMemcpyDeviceToHost, s.stream));
         if (bwd) QDH_CUDA(cudaMemcpyAsync(hgout + off, s.gout, bytes, cudaMemcpyDeviceToHost, s.stream));
     }
-    for (int i = 0; i < kSlots; ++i) QDH_CUDA(cudaStreamSynchronize(c->slot[i].stream));
+    for (int i = 0; i < n_slots; ++i) QDH_CUDA(cudaStreamSynchronize(c->slot[i].stream));
     QDH_CUDA(cudaGetLastError());
     return QD_OK;
 }

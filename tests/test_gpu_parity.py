@@ -539,6 +539,24 @@ def test_host_buffer_capi_pipeline(Q):
         q.zero_()
         N.check(N.lib().qd_uniform_fwd_host(N.ptr(x), N.ptr(q), n, b, 16, torch.cuda.current_device()))
         assert torch.equal(q, qd.cpu())
+    # min/max backward is row-local, so the host entry point equals the resident call bit for bit whatever the staging:
+    # one launch straight on the pinned buffers (<= 8 Mi elements), the chunked pipeline (larger, or pageable memory)
+    for n, b, pinned in ((1000, 256, True), (1_000_003, 256, True), (3_000_000, 1000, True), (2_000_001, 256, False),
+                         (30_000_001, 256, True), (26_000_123, 1000, True)):
+        pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+        x = pin(torch.from_numpy((rng.standard_normal(n) * 0.05).astype(np.float32)))
+        g = pin(torch.from_numpy(rng.standard_normal(n).astype(np.float32)))
+        q = pin(torch.zeros(n, dtype=torch.float32))
+        go = pin(torch.zeros(n, dtype=torch.float32))
+        N.check(N.lib().qd_uniform_fwd_bwd_host(N.ptr(x), N.ptr(g), N.ptr(q), N.ptr(go), n, b, 16, N.BWD_MINMAX,
+                                                torch.cuda.current_device()))
+        xd, gd = x.cuda(), g.cuda()
+        qd, god = torch.empty_like(xd), torch.empty_like(gd)
+        ws = N.workspace(n, b, xd.device)
+        N.check(N.lib().qd_uniform_fwd_bwd(N.ptr(xd), N.ptr(gd), N.ptr(qd), N.ptr(god), n, b, 16, N.BWD_MINMAX, N.ptr(ws), ws.numel(),
+                                           N.stream_ptr()))
+        assert torch.equal(q, qd.cpu()), (n, b)
+        assert torch.equal(go, god.cpu()), (n, b)
 
 
 def test_multi_tensor_plan_matches_per_tensor(Q):
