@@ -67,5 +67,21 @@ for kind in ("absmax", "absnorm"):
         sfa = Q.ScalingFunction(kind, False, False, bucket, False)
         sfa.inv_scale_down(sfa.scale_down(src[2]))
 QF.ALLOW_UNPINNED_SCALING = False
+# tiled helper kernels past one tile per thread-group (full-tile fast paths + general tails), 1 / 2 / 4 / 8-bit codes
+from quantized_distillation_b200 import _native as N  # noqa: E402
+xb = torch.randn(70_001).cuda() * 0.05
+for s_levels, bucket in ((2, 256), (4, 100), (16, 256), (256, 1000), (16, None)):
+    assert torch.equal(codec.decode(codec.encode_uniform(xb, s_levels, bucket)), Q.uniformQuantization(xb, s_levels, bucket_size=bucket)[0])
+sfb = Q.ScalingFunction("linear", False, False, 256, False)
+sfb.inv_scale_down(sfb.scale_down(xb))
+# host entry points: one launch on pinned host pointers (small), chunked pipeline (pageable memory)
+for pinned in (True, False):
+    m = 300_001
+    hx, hg = torch.randn(m) * 0.05, torch.randn(m)
+    hq, hgo = torch.zeros(m), torch.zeros(m)
+    if pinned:
+        hx, hg, hq, hgo = hx.pin_memory(), hg.pin_memory(), hq.pin_memory(), hgo.pin_memory()
+    N.check(N.lib().qd_uniform_fwd_bwd_host(N.ptr(hx), N.ptr(hg), N.ptr(hq), N.ptr(hgo), m, 256, 16, N.BWD_MINMAX, 0))
+    assert torch.equal(hq, Q.uniformQuantization(hx.cuda(), 16, bucket_size=256)[0].cpu())
 torch.cuda.synchronize()
 print("sanitize probe ok")
