@@ -500,6 +500,13 @@ def main():
         run_reference_arm(args)
         return
 
+    # stdout carries ONE JSON line.  Libraries write there too (NCCL prints its version line to stdout when the box
+    # sets NCCL_DEBUG=VERSION, and ignores NCCL_DEBUG_FILE at that level), so file descriptor 1 points at stderr for
+    # the duration of the run and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from quantized_distillation_b200 import _native as N
@@ -674,10 +681,12 @@ def main():
     if args.sweep and rank == 0:
         from tools import sweep
         out["sweep_file"] = sweep.run(dev)
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    os.close(real_stdout)
 
 
 if __name__ == "__main__":

@@ -55,3 +55,21 @@ def test_gpu_arm_has_no_cpu_fallback():
         pytest.skip("GPU present")
     res = run(["--steps", "1", "--warmup", "1", "--train", "none", "--no-cpu"])
     assert res.returncode != 0 and "CUDA" in (res.stderr + res.stdout)
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_exactly_one_json_line():
+    """stdout of the GPU arm is ONE line (library chatter, e.g. NCCL's version line, goes to stderr) with the contract keys."""
+    res = run(["--steps", "5", "--warmup", "3", "--train", "none", "--no-cpu", "--e2e-steps", "2"])
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = res.stdout.splitlines()
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in d, key
+    assert d["steps"] == 5 and d["gpu_launches"] == 5 and d["n_gpus"] == 1
+    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.2
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 2 * 4 * d["config"]["elements"] == e["d2h_bytes_per_step"]
+    assert 0 < e["value"] < e["copy_ceiling"]["value"] * 1.05          # the pipeline cannot beat two plain copies by more than noise
