@@ -22,7 +22,11 @@ LABELS = {"warp_rows_kernel<2, (int)-1, 2, 1": "uniform fwd, bucket 256", "warp_
           "grid_apply": "grid path (bucket None): apply", "staged_rows_kernel<2, (int)-1": "staged path: uniform fwd",
           "staged_rows_kernel<2, 2": "staged path: fused fwd + min/max bwd", "staged_rows_kernel<3": "staged path: centroid op",
           "plan_sgd_step_kernel": "fused SGD + fix-up + re-quantize (plan)", "plan_nonuniform_fwd_kernel": "centroid plan forward",
-          "plan_rows_kernel": "uniform plan", "block_rows_kernel": "block path (round-1 kernel)"}
+          "plan_rows_kernel": "uniform plan", "block_rows_kernel": "block path (round-1 kernel)",
+          "unpack_dequant_kernel<1, 4>": "packed codec: 4-bit codes -> dequantized float32 (uniform)",
+          "unpack_dequant_kernel<0, 4>": "packed codec: 4-bit codes -> dequantized float32 (centroids)",
+          "pack_kernel<4>": "packed codec: uint8 codes -> 4-bit", "inv_scale_kernel": "inverse scaling alone",
+          "centroid_index_kernel": "pre-scaled index search"}
 BASE = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -58,7 +62,7 @@ def main(rep, out_md, traffic_json=None):
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
         key = (name, r[col["launch__grid_size"]] if "launch__grid_size" in col else "")
-        if key in seen or not any(k in name for k in ("rows_kernel", "points_grad", "grid_", "plan_", "select_")):
+        if key in seen or not any(k in name for k in ("rows_kernel", "points_grad", "grid_", "plan_", "select_", "pack_", "unpack_", "inv_scale", "centroid_index")):
             continue
         seen.add(key)
         stalls = sorted(((num(r, c), c.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")) for c in stall_cols), reverse=True)[:4]
