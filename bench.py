@@ -442,6 +442,19 @@ def train_legs(which, world, rank, dev, steps, with_cpu):
             cands.append(leg["cuda_graph_fused_optimizer"])
         best = max(cands, key=lambda r: r["steps_per_s"])
         leg["steps_per_s"], leg["images_per_s"], leg["ms_per_step"] = best["steps_per_s"], best["images_per_s"], best["ms_per_step"]
+        # The model's convolutions are cuDNN's, in torch's default math mode: TF32 on the tensor cores
+        # (torch.backends.cudnn.allow_tf32 = True) -- the mode the reference's own code gets under this torch, and the one
+        # the reference-style baseline below runs in.  The quantization kernels are float32 throughout.  The same leg with
+        # TF32 switched off (IEEE float32 convolutions, what the reference's 2018 stack computed) is reported next to it.
+        leg["convolution_math"] = "torch default: TF32 (cudnn.allow_tf32=True); matmuls float32"
+        tf32_was = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            strict = run_train_leg(kind, world, rank, dev, max(6, wsteps // 2), 5, graph=True, fused=kind != "diffquant")
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32_was
+        leg["strict_fp32_convolutions"] = {k: strict[k] for k in ("steps_per_s", "ms_per_step", "images_per_s", "steps", "warmup",
+                                                                  "cuda_graph_step", "captured")}
         if world == 1 and rank == 0:
             leg["reference_style_gpu"] = reference_style_leg(kind, dev, max(6, wsteps // 2), 3)
             leg["reference_style_steps_per_s"] = leg["reference_style_gpu"]["steps_per_s"]
