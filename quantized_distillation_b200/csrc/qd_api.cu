@@ -602,7 +602,7 @@ extern "C" int qd_nonuniform_bwd(const float* g, const uint8_t* idx_u8, const in
     else
         points_grad_partial<int64_t><<<grid, kPgThreads, smem, s>>>(g, idx_i64, alpha, num_points, geo, partial);
     QD_CUDA(cudaGetLastError());
-    points_grad_final<<<1, 256, 0, s>>>(partial, grid, num_points, grad_points);
+    points_grad_final<<<num_points, 256, 0, s>>>(partial, grid, num_points, grad_points);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }

@@ -137,15 +137,23 @@ __global__ void __launch_bounds__(kPgThreads) points_grad_partial(const float* _
     }
 }
 
-// one warp per centroid: lanes stride over the CTA partials, then a fixed shuffle tree
+// one CTA per centroid: 256 threads stride over the CTA partials (a few loads each, all in flight), then a fixed
+// tree (lanes by shuffle, warps in order).  One warp per centroid on ONE CTA made this kernel 6 us (K = 4) to 18 us
+// (K = 16) of serial L2 round trips -- a quarter of the whole op at 64 Mi elements.
 __global__ void __launch_bounds__(256) points_grad_final(const double* __restrict__ partial, int nblocks, int K,
                                                          float* __restrict__ out) {
+    __shared__ double s_w[8];
+    const int k = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < K; k += (int)(blockDim.x >> 5)) {
-        double s = 0.0;
-        for (int b = lane; b < nblocks; b += 32) s += partial[(int64_t)b * K + k];
-        s = warp_sum(s);
-        if (lane == 0) out[k] = (float)s;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * K + k];
+    s = warp_sum(s);
+    if (lane == 0) s_w[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        out[k] = (float)t;
     }
 }
 
