@@ -166,7 +166,10 @@ class FlatDataParallel(torch.nn.Module):
     def reduce_gradients(self):
         """Average of the flat gradient over the replicas.  Buckets whose all-reduce was already issued from
         the backward pass are only waited for; the others (single-bucket models, parameters that took no
-        part in the backward pass) are reduced now."""
+        part in the backward pass) are reduced now.  The call closes the step: every bucket is re-armed for
+        the next backward pass, so a loop that clears gradients through its optimizer instead of this
+        wrapper's ``zero_grad()`` still reduces every step.  (One backward pass per reduction: a second
+        one before this call would accumulate into buckets that are already averaged.)"""
         if self.world == 1:
             return
         for bucket in self._buckets:
@@ -174,6 +177,8 @@ class FlatDataParallel(torch.nn.Module):
                 self._send(bucket)
         if self._comm_stream is not None:
             torch.cuda.current_stream(self.flat_grad.device).wait_stream(self._comm_stream)
+        for bucket in self._buckets:
+            bucket["pending"], bucket["sent"] = len(bucket["members"]), False
 
 
 def wrap_data_parallel(model, device=None, flat=True, bucket_mb=32.0):

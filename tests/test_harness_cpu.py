@@ -151,9 +151,23 @@ def _flat_worker(rank, world, port, ret):
     flat = torch.cat([p.detach().view(-1) for p in model.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(w)]
     torch.distributed.all_gather(gathered, flat)
-    ret[rank] = bool(torch.equal(gathered[0], gathered[1]))
+    ok = bool(torch.equal(gathered[0], gathered[1]))
     if r == 0:
         ret["params"] = flat.clone()
+    # two hand-written steps that clear the gradients through the OPTIMIZER, never through the wrapper's
+    # zero_grad(): reduce_gradients() itself re-arms the buckets, so the second step is reduced as well
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    for step in range(2):
+        opt.zero_grad(set_to_none=False)
+        x, y = local[step]
+        F.cross_entropy(model(x), y).backward()
+        model.reduce_gradients()
+        assert all(b["sent"] is False and b["pending"] == len(b["members"]) for b in model._buckets)
+        g = model.flat_grad.clone()
+        both = [torch.zeros_like(g) for _ in range(w)]
+        torch.distributed.all_gather(both, g)
+        ok = ok and bool(torch.equal(both[0], both[1])) and bool(g.abs().sum() > 0)
+    ret[rank] = ok
     torch.distributed.destroy_process_group()
 
 
