@@ -21,6 +21,10 @@
  *     `xhat` output of qd_scale_down, whose length is padded_len.
  *   - per-row outputs (alpha, beta: float32[rows]; argmin, argmax: int64[rows],
  *     index inside the row, first occurrence) may be NULL when not wanted.
+ *   - device: kernels launch on the calling thread's CURRENT CUDA device (one
+ *     process per GPU is the deployment model); the device pointers and
+ *     `stream` of a call must belong to it.  Only the *_host entry points take
+ *     a device ordinal and switch (and restore) the device themselves.
  *   - `stream` is a cudaStream_t; every call only enqueues work on it (no host
  *     synchronisation) except the *_host entry points, which return after the
  *     result is in host memory.

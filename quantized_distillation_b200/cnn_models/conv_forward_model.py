@@ -167,7 +167,8 @@ class WeightQuantizer:
     (closures at :235-266) lifted to an object that owns the multi-tensor plan."""
 
     def __init__(self, model, numBits, bucket_size, quantizationFunctionToUse="uniformLinearScaling",
-                 backprop_quantization_style="none", quantize_first_and_last_layer=True):
+                 backprop_quantization_style="none", quantize_first_and_last_layer=True, *, stochastic_rounding=False,
+                 max_element=False, subtract_mean=False):
         style = "none" if backprop_quantization_style is None else backprop_quantization_style.lower()
         if style not in ("none", "truncated", "complicated"):
             raise ValueError("The specified backprop_quantization_style not recognized")
@@ -175,6 +176,21 @@ class WeightQuantizer:
         self.s, self.scaling = _uniform_levels(quantizationFunctionToUse, numBits)
         self.bucket_size = bucket_size
         self.params = _selected_parameters(model, quantize_first_and_last_layer)
+        # the options only the NMT loop passes (translation_models/model.py:162-164, 198-204: stochasticRounding,
+        # maxElementAllowedForQuantization, subtractMeanInQuantization); the multi-tensor plan is the plain
+        # deterministic op, so any of them selects the per-tensor fused kernel, which implements all three
+        self.options = {"stochastic_rounding": bool(stochastic_rounding), "max_element": max_element,
+                        "subtract_mean": bool(subtract_mean)}
+        extra = self.options["stochastic_rounding"] or max_element is not False or self.options["subtract_mean"]
+        if extra and self.scaling == "linear":
+            if style == "complicated":
+                # reference: backward raises for subtract_mean (quant_functions.py:329-330) and re-runs its forward with
+                # max_element / stochastic rounding (:341-347), which the backward kernel does not take
+                raise NotImplementedError("backprop_quantization_style 'complicated' is not available together with "
+                                          "stochastic_rounding / max_element / subtract_mean")
+            self.plan = None
+            self._master = [torch.empty_like(p.data) for p in self.params]
+            return
         if self.scaling != "linear":
             # 'uniformAbsMaxScaling' (:206-208) cannot execute in the reference; the intended semantics are an opt-in
             # extension without a parity target (quantization.quant_functions.ALLOW_UNPINNED_SCALING), per tensor
@@ -193,12 +209,12 @@ class WeightQuantizer:
         if self.style == "truncated":
             torch._foreach_clamp_min_([p.data for p in self.params], -1.0)   # p.data.clamp_(-1, 1), reference :240-241
             torch._foreach_clamp_max_([p.data for p in self.params], 1.0)
-        if self.plan is None:                                                 # absmax extension: one fused launch per tensor
+        if self.plan is None:                                  # NMT-loop options / absmax extension: one fused launch per tensor
             if save:
                 torch._foreach_copy_(self._master, [p.data for p in self.params])
             for p in self.params:
                 quantization.uniformQuantization(p.data, self.s, type_of_scaling=self.scaling, bucket_size=self.bucket_size,
-                                                 modify_in_place=True)
+                                                 modify_in_place=True, **self.options)
             return
         if save:
             self.plan.save_and_quantize_()          # shadow copy + in-place quantization, one launch

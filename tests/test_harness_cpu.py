@@ -87,6 +87,59 @@ def test_train_model_without_quantization_runs_on_cpu():
         cfm.train_model(m, data, data, use_distillation_loss=True)
 
 
+def test_weight_quantizer_nmt_loop_options_choreography(monkeypatch):
+    """The options only the NMT loop passes (translation_models/model.py:162-164, 198-204, 247-279: stochastic rounding,
+    max_element, subtract_mean) select WeightQuantizer's per-tensor path.  Its save / quantize-in-place / restore /
+    truncated fix-up choreography is host logic: checked here with the fused op replaced by the oracle (the op itself
+    with these options is GPU-tested in tests/test_gpu_parity.py)."""
+    import numpy as np
+    from oracle import quant_oracle as O
+    seen = []
+
+    def oracle_op(tensor, s, type_of_scaling="linear", stochastic_rounding=False, max_element=False, subtract_mean=False,
+                  bucket_size=None, modify_in_place=False):
+        seen.append((type_of_scaling, stochastic_rounding, max_element, subtract_mean, bucket_size, modify_in_place))
+        q = O.uniform_fwd(tensor.numpy().reshape(-1), s, bucket_size, subtract_mean=subtract_mean, max_element=max_element)[0]
+        tensor.copy_(torch.from_numpy(np.ascontiguousarray(q)).view(tensor.shape))
+        return tensor, None
+
+    monkeypatch.setattr(cfm.quantization, "uniformQuantization", oracle_op)
+    torch.manual_seed(3)
+    model = student()
+    params = list(model.parameters())
+    with torch.no_grad():
+        params[2].view(-1)[:7] = 3.0                                 # 'truncated' clamps the weights to [-1, 1] first (:240-241)
+    wq = cfm.WeightQuantizer(model, numBits=4, bucket_size=256, backprop_quantization_style="truncated",
+                             quantize_first_and_last_layer=False, max_element=0.5, subtract_mean=True)
+    assert wq.plan is None and len(wq.params) == len(params) - 2
+    before = [p.detach().clone() for p in params]
+    wq.quantize_weights_model()
+    assert len(seen) == len(wq.params) and all(c == ("linear", False, 0.5, True, 256, True) for c in seen)
+    for i, (p, o) in enumerate(zip(params, before)):
+        if i in (0, len(params) - 1):
+            assert torch.equal(p, o)                                  # first / last tensor left alone (:237-239)
+        else:
+            want = O.uniform_fwd(o.clamp(-1, 1).numpy().reshape(-1), 16, 256, subtract_mean=True, max_element=0.5)[0]
+            assert np.array_equal(p.detach().numpy().reshape(-1).view(np.uint32), np.asarray(want).reshape(-1).view(np.uint32))
+    wq.restore_weights_model()
+    for i, (p, o) in enumerate(zip(params, before)):
+        assert torch.equal(p, o if i in (0, len(params) - 1) else o.clamp(-1, 1))     # the clamp persists, like in the reference
+    with torch.no_grad():
+        params[3].view(-1)[:5] = -2.0
+    for p in params:
+        p.grad = torch.ones_like(p)
+    wq.backward_quant_weights_model()                                 # p.grad[|p| > 1] = 0 (:263-264)
+    assert float(params[3].grad.view(-1)[:5].abs().sum()) == 0.0 and float(params[3].grad.sum()) == params[3].numel() - 5
+    assert all(bool((p.grad == 1).all()) for i, p in enumerate(params) if i != 3)
+    # stochastic rounding is passed through; 'complicated' refuses the three options like the reference's backward does
+    seen.clear()
+    cfm.WeightQuantizer(model, 2, 256, stochastic_rounding=True).quantize_weights_model(save=False)
+    assert seen and all(c[1] is True and c[2] is False and c[3] is False for c in seen)
+    for opt in ({"stochastic_rounding": True}, {"max_element": 1.0}, {"subtract_mean": True}):
+        with pytest.raises(NotImplementedError):
+            cfm.WeightQuantizer(model, 4, 256, backprop_quantization_style="complicated", **opt)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
