@@ -107,6 +107,22 @@ static int resident_ctas(K kernel, int threads, size_t smem) {
     return n;
 }
 
+// Opts a kernel instantiation into `smem` bytes of dynamic shared memory.  The attribute only ever grows (per
+// instantiation and device: `opted` is that instantiation's own table) and changes under the library mutex, so two
+// host threads launching the same instantiation with different row lengths can never lower it between the other
+// thread's opt-in and its launch.
+template <typename K>
+static int opt_in_smem(K kernel, size_t smem, size_t* opted) {
+    int d = 0;
+    QD_CUDA(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (smem > opted[d & 63]) {
+        QD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted[d & 63] = smem;
+    }
+    return QD_OK;
+}
+
 // ------------------------------------------------------------------ geometry / workspace
 extern "C" int qd_bucket_geometry(int64_t n, int64_t bucket, int64_t* rows, int64_t* row_len, int64_t* padded_len) {
     Geometry g;
@@ -188,7 +204,11 @@ static int launch_block_inst(const Params& P, cudaStream_t s) {
     auto kern = block_rows_kernel<OP, BWD, STAGED, GROUP>;
     const size_t smem = STAGED ? (size_t)P.geo.row_len * sizeof(float) : 0;
     if (smem + 8192 > di->smem_optin) return fail(QD_ERR_UNSUPPORTED, "row of %lld floats does not fit in shared memory", (long long)P.geo.row_len);
-    if (STAGED) QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (STAGED) {
+        static size_t opted[64] = {};  // largest dynamic size this instantiation was opted into, per device
+        rc = opt_in_smem(kern, smem, opted);
+        if (rc) return rc;
+    }
     const int occ = resident_ctas(kern, kBlockCtaThreads, smem);
     constexpr int64_t rows_per_cta = kBlockCtaThreads / GROUP;
     int64_t need = (P.geo.rows + rows_per_cta - 1) / rows_per_cta;
@@ -216,12 +236,8 @@ static int launch_staged_inst(const Params& P, cudaStream_t s) {
     const size_t smem = (size_t)STAGES * stage_floats * sizeof(float);
     if (smem + 8192 > di->smem_optin) return fail(QD_ERR_UNSUPPORTED, "row of %lld floats does not fit in shared memory", (long long)P.geo.row_len);
     static size_t opted[64] = {};  // largest dynamic size this instantiation was opted into, per device
-    int d = 0;
-    cudaGetDevice(&d);
-    if (smem > opted[d & 63]) {
-        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        opted[d & 63] = smem;
-    }
+    rc = opt_in_smem(kern, smem, opted);
+    if (rc) return rc;
     const int occ = resident_ctas(kern, T, smem);
     const int64_t cap = (int64_t)di->sms * occ;
     const int grid = (int)(P.geo.rows < cap ? P.geo.rows : cap);
