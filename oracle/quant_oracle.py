@@ -12,7 +12,9 @@ Pinning: the reference holds no tests or golden vectors for this path
 (SURVEY.md section 4), so the oracle is pinned against the reference *itself*:
 ``tests/golden/make_golden.py`` imports ``/root/reference/quantization``
 unmodified, runs it on seeded inputs and stores input/output pairs under
-``tests/golden/``; ``tests/test_oracle_golden.py`` checks every function below
+``tests/golden/`` (``make_golden_options.py`` does the same for ``subtract_mean``,
+``max_element`` and stochastic rounding with the reference's own ``torch.rand``
+draws); ``tests/test_oracle_golden.py`` checks every function below
 bit-for-bit (tolerance only where the reference itself sums in a different
 order) against those fixtures.
 
@@ -68,13 +70,17 @@ def bucketed(x: np.ndarray, bucket_size) -> np.ndarray:
 # --------------------------------------------------------------------------
 # a2 / a3: linear scaling and its inverse (quant_functions.py:56-107, 131-152)
 # --------------------------------------------------------------------------
-def pre_ops(x: np.ndarray, subtract_mean=False, max_element=False):
-    """Optional global mean subtraction and clamp (quant_functions.py:66-74)."""
+def pre_ops(x: np.ndarray, subtract_mean=False, max_element=False, mean=None):
+    """Optional global mean subtraction and clamp (quant_functions.py:66-74).  ``mean`` overrides the
+    computed mean: the reference's is a float32 torch reduction whose last bit depends on the summation
+    order, so everything AFTER the mean is pinned bit for bit by handing the reference's own value in
+    (tests/test_oracle_golden.py), and the mean itself within a summation-order tolerance."""
     flat = np.asarray(x, dtype=F32).reshape(-1).copy()
-    mean = F32(0)
     if subtract_mean:
-        mean = F32(flat.mean(dtype=np.float64))  # order-dependent in the reference: tolerance only
+        mean = F32(flat.mean(dtype=np.float64)) if mean is None else F32(mean)   # order-dependent in the reference
         flat = flat - mean
+    else:
+        mean = F32(0)
     if max_element is not False:
         m = F32(max_element)
         flat = np.minimum(np.maximum(flat, -m), m)
@@ -93,11 +99,11 @@ def bucket_stats(rows: np.ndarray):
     return alpha, beta.astype(F32), argmin, argmax
 
 
-def scale_down(x, bucket_size, subtract_mean=False, max_element=False):
+def scale_down(x, bucket_size, subtract_mean=False, max_element=False, mean=None):
     """x_hat = (x - beta) / alpha: subtract, then true division
     (quant_functions.py:106-107).  Returns the padded (rows, row_len) array and
     the per-row state the reference keeps on the ScalingFunction object."""
-    flat, mean = pre_ops(x, subtract_mean, max_element)
+    flat, mean = pre_ops(x, subtract_mean, max_element, mean)
     rows = bucketed(flat, bucket_size)
     alpha, beta, argmin, argmax = bucket_stats(rows)
     xh = ((rows - beta[:, None]).astype(F32) / alpha[:, None]).astype(F32)
@@ -122,10 +128,10 @@ def uniform_levels(xh: np.ndarray, s: int) -> np.ndarray:
     return np.rint((xh * S).astype(F32)).astype(F32)
 
 
-def uniform_fwd(x, s: int, bucket_size, subtract_mean=False, max_element=False):
+def uniform_fwd(x, s: int, bucket_size, subtract_mean=False, max_element=False, mean=None):
     """Returns (q, idx, state).  q = ((idx/S)*alpha + beta) (+mean), each op
     rounded to float32 (quant_functions.py:189-193, 142-148)."""
-    xh, st = scale_down(x, bucket_size, subtract_mean, max_element)
+    xh, st = scale_down(x, bucket_size, subtract_mean, max_element, mean)
     S = F32(s - 1)
     lvl = uniform_levels(xh, s)
     q = inv_scale_down((lvl / S).astype(F32), st)
@@ -133,10 +139,10 @@ def uniform_fwd(x, s: int, bucket_size, subtract_mean=False, max_element=False):
     return q, idx, st
 
 
-def uniform_fwd_stochastic(x, s: int, bucket_size, u: np.ndarray):
+def uniform_fwd_stochastic(x, s: int, bucket_size, u: np.ndarray, subtract_mean=False, max_element=False, mean=None):
     """Stochastic rounding given the uniform draws ``u`` (padded layout):
     floor(x_hat*S)/S + [u <= frac]/S (quant_functions.py:179-187)."""
-    xh, st = scale_down(x, bucket_size)
+    xh, st = scale_down(x, bucket_size, subtract_mean, max_element, mean)
     S = F32(s - 1)
     prob = (S * xh).astype(F32)
     fl = np.floor(prob).astype(F32)
@@ -265,9 +271,9 @@ def nonuniform_index_nearest(xh: np.ndarray, points: np.ndarray) -> np.ndarray:
     return (i - step).astype(np.int64).reshape(xh.shape)
 
 
-def nonuniform_fwd(x, points, bucket_size, rule="nearest"):
-    """Returns (q, idx, state); q = k[idx]*alpha + beta (quant_functions.py:278-289)."""
-    xh, st = scale_down(x, bucket_size)
+def nonuniform_fwd(x, points, bucket_size, rule="nearest", subtract_mean=False, max_element=False, mean=None):
+    """Returns (q, idx, state); q = k[idx]*alpha + beta (+ mean) (quant_functions.py:278-289)."""
+    xh, st = scale_down(x, bucket_size, subtract_mean, max_element, mean)
     k = np.asarray(points, dtype=F32)
     idx = nonuniform_index_nearest(xh, k) if rule == "nearest" else nonuniform_index_midpoint(xh, k)
     q = inv_scale_down(k[idx], st)

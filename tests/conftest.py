@@ -38,3 +38,18 @@ def golden():
         family, key, kind, n, b, s = str(row).split("|")
         cases.setdefault(family, []).append(dict(key=key, kind=kind, n=int(n), bucket=None if int(b) < 0 else int(b), s=int(s)))
     return data, cases
+
+
+@pytest.fixture(scope="session")
+def golden_options():
+    """Reference outputs for the options only the NMT loop passes (subtract_mean, max_element, stochastic
+    rounding with the reference's own draws): tests/golden/make_golden_options.py."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "reference_vectors_options.npz")
+    data = np.load(path)
+    cases = {}
+    for row in data["meta"]:
+        family, key, kind, n, b, s, sub, mx = str(row).split("|")
+        cases.setdefault(family, []).append(dict(key=key, kind=kind, n=int(n), bucket=None if int(b) < 0 else int(b), s=int(s),
+                                                 subtract_mean=bool(int(sub)), max_element=False if mx == "no" else float(mx)))
+    return data, cases

@@ -166,3 +166,70 @@ def test_c_oracle_matches_golden(golden):
         k = c["key"]
         out = CO.uniform_bwd_minmax(data[k + "_x"], data[k + "_g"], c["s"], c["bucket"])
         assert np.abs(out - data[k + "_gout"]).max() <= 1e-6 * np.abs(data[k + "_g"]).sum() / c["s"] + 1e-7
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the options only the NMT loop passes (translation_models/model.py:162-164): fixtures of make_golden_options.py
+# ----------------------------------------------------------------------------------------------------------------
+def _mean_close(x, got, ref):
+    """The reference's mean is a float32 torch reduction: equal to the float64 mean up to the summation order."""
+    x64 = np.asarray(x, dtype=np.float64)
+    assert abs(float(got) - float(ref)) <= 1e-6 * np.abs(x64).mean() + 1e-30, (float(got), float(ref))
+
+
+def test_pre_ops_uniform_forward_bit_exact(golden_options):
+    data, cases = golden_options
+    assert len(cases["pre_uniform"]) >= 200
+    clamped = 0
+    for c in cases["pre_uniform"]:
+        k, x = c["key"], data[c["key"] + "_x"]
+        ref_mean = data[k + "_mean"][0]
+        opts = dict(subtract_mean=c["subtract_mean"], max_element=c["max_element"])
+        # everything downstream of the mean, bit for bit, given the reference's own mean ...
+        q, idx, st = O.uniform_fwd(x, c["s"], c["bucket"], mean=ref_mean, **opts)
+        eq(q, data[k + "_q"])
+        eq(st["alpha"], data[k + "_alpha"])
+        eq(st["beta"], data[k + "_beta"])
+        eq(st["argmin"], data[k + "_argmin"])
+        eq(st["argmax"], data[k + "_argmax"])
+        xh, st2 = O.scale_down(x, c["bucket"], mean=ref_mean, **opts)
+        eq(xh.reshape(-1), data[k + "_xhat"])
+        if k + "_inv_in" in data.files:                                  # inverse adds the mean back (:148)
+            eq(O.inv_scale_down(data[k + "_inv_in"].reshape(xh.shape), st2).reshape(-1), data[k + "_inv_out"])
+        # ... and the oracle's own mean inside the summation-order tolerance
+        if c["subtract_mean"]:
+            _mean_close(x, O.pre_ops(x, True, False)[1], ref_mean)
+        else:
+            assert ref_mean == 0
+        if c["max_element"] is not False:
+            clamped += int((np.abs(x - ref_mean) > c["max_element"]).any())
+    assert clamped >= 100                                                 # the clamp is active in most clamp cases
+
+
+def test_pre_ops_nonuniform_direct_path_bit_exact(golden_options):
+    data, cases = golden_options
+    assert len(cases["pre_nonuniform"]) >= 40
+    for c in cases["pre_nonuniform"]:
+        k = c["key"]
+        q, idx, st = O.nonuniform_fwd(data[k + "_x"], data[k + "_points"], c["bucket"], rule="nearest", mean=data[k + "_mean"][0],
+                                      subtract_mean=c["subtract_mean"], max_element=c["max_element"])
+        eq(idx.reshape(-1).astype(np.int64), data[k + "_idx"].reshape(-1).astype(np.int64))
+        eq(q, data[k + "_q"])
+
+
+def test_stochastic_rounding_given_the_reference_draws_bit_exact(golden_options):
+    """quant_functions.py:174-187 with the very ``torch.rand`` array the reference drew: floor, fraction, ``u <= frac``
+    (equality included), the 1/s bump and the padded layout of ``u`` are all pinned; only the draw itself is random."""
+    data, cases = golden_options
+    assert len(cases["stochastic"]) >= 80
+    ups = total = 0
+    for c in cases["stochastic"]:
+        k, x, u = c["key"], data[c["key"] + "_x"], data[c["key"] + "_u"]
+        q, st = O.uniform_fwd_stochastic(x, c["s"], c["bucket"], u, subtract_mean=c["subtract_mean"], max_element=c["max_element"],
+                                         mean=data[k + "_mean"][0])
+        eq(q, data[k + "_q"])
+        # not vacuous: the rounded-up fraction is neither 0 nor 1
+        det = O.uniform_fwd(x, c["s"], c["bucket"], subtract_mean=c["subtract_mean"], max_element=c["max_element"], mean=data[k + "_mean"][0])[0]
+        ups += int((q != det).sum())
+        total += q.size
+    assert 0.1 < ups / total < 0.9
