@@ -207,14 +207,20 @@ def shard_batches(batches, rank, world):
 
 
 def convert_state_dict_to_data_parallel(state_dict):
-    """Adds the ``module.`` prefix a (Distributed)DataParallel wrapper expects
+    """Adds the ``module.`` prefix a (Distributed)DataParallel wrapper expects, to every key
     (reference: helpers/functions.py:179-189)."""
-    return OrderedDict((k if k.startswith("module.") else "module." + k, v) for k, v in state_dict.items())
+    return OrderedDict(("module." + k, v) for k, v in state_dict.items())
 
 
 def convert_state_dict_from_data_parallel(state_dict):
-    """Strips the ``module.`` prefix (reference: helpers/functions.py:191-205)."""
-    return OrderedDict((k[len("module."):] if k.startswith("module.") else k, v) for k, v in state_dict.items())
+    """Strips the ``module.`` prefix; a key without it raises ``ValueError`` like the reference
+    (helpers/functions.py:191-205)."""
+    out = OrderedDict()
+    for k, v in state_dict.items():
+        if not k.startswith("module."):
+            raise ValueError("The state_dict passed was not saved by a data parallel instance")
+        out[k[len("module."):]] = v
+    return out
 
 
 def gpu_numa_cpus(device_index: int):

@@ -173,3 +173,50 @@ def test_compiled_front_door_builds_and_refuses_cpu_tensors():
     assert mod is not None and hasattr(mod, "uniform_fwd") and hasattr(mod, "uniform_bwd")
     with pytest.raises(RuntimeError):
         mod.uniform_fwd(torch.zeros(16), 16, 0, False)
+
+
+def test_host_helpers_match_reference_executed_fixtures():
+    """The host-side helpers around the hot path against outputs of the reference's own functions
+    (tests/golden/make_golden_host.py -> reference_host_logic.json): bit allocation, Huffman code, bucket view,
+    learning-rate schedules, size accounting, state-dict prefixes."""
+    import json
+    import math
+    from collections import OrderedDict
+    from quantized_distillation_b200 import codec, distributed as D
+    from quantized_distillation_b200.cnn_models import help_fun as hf
+    from quantized_distillation_b200.quantization import help_functions as H
+    with open(os.path.join(ROOT, "tests", "golden", "reference_host_logic.json")) as f:
+        ref = json.load(f)
+
+    for c in ref["assign_bits_automatically"]:
+        init = c["initial"] if isinstance(c["initial"], int) else list(c["initial"])
+        assert H.assign_bits_automatically(list(c["norms"]), init, input_is_point=c["input_is_point"]) == c["result"]
+
+    for c in ref["huffman_encode"]:
+        freq = {int(s): f for s, f in c["freq"]}
+        assert [[s, bits] for s, bits in H.huffman_encode(freq)] == [[int(s), bits] for s, bits in c["code"]]
+
+    for c in ref["create_bucket_tensor"]:
+        t = torch.arange(c["n"], dtype=torch.float32) * 0.5 - 3
+        r = H.create_bucket_tensor(t.clone(), c["bucket"], fill_values=c["fill"])
+        assert list(r.shape) == c["shape"], c
+        tail = [None if v != v else v for v in r.reshape(-1)[-8:].tolist()]
+        assert tail == c["tail"], c
+
+    for c in ref["learning_rate_scheduler"]:
+        sch = hf.LearningRateScheduler(c["initial"], c["style"])
+        for epoch, err, lr, stop in c["trace"]:
+            got_lr, got_stop = sch.update_learning_rate(epoch, err)
+            assert got_lr == lr and bool(got_stop) == stop, (c["style"], epoch, got_lr, lr, got_stop, stop)
+
+    for c in ref["get_size_reduction"]:
+        assert math.isclose(codec.get_size_reduction(c["bits"], bucket_size=c["bucket"], full_precision_bits=c["full"]), c["result"],
+                            rel_tol=0, abs_tol=0), c
+
+    p = ref["state_dict_prefix"]
+    sd = OrderedDict((k, 0) for k in p["keys"])
+    wrapped = D.convert_state_dict_to_data_parallel(sd)
+    assert list(wrapped) == p["to"] and list(D.convert_state_dict_from_data_parallel(wrapped)) == p["from_of_to"]
+    assert p["from_with_unprefixed_key"] == "ValueError"
+    with pytest.raises(ValueError):
+        D.convert_state_dict_from_data_parallel(sd)
