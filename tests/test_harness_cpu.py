@@ -252,3 +252,37 @@ def test_state_dict_prefix_helpers():
     assert list(D.convert_state_dict_from_data_parallel(wrapped)) == list(sd)
     with pytest.raises(ValueError):
         D.shard_batches([(torch.zeros(5, 3), torch.zeros(5))], 0, 2)
+
+
+def test_models_match_reference_built_fixtures():
+    """ConvolForwardNet / Wide_ResNet against the reference's own classes (tests/golden/make_golden_models.py builds them
+    from /root/reference in small configurations): same parameter and state-dict order -- the hot path quantizes
+    ``parameters()`` in that order and ``quantize_first_and_last_layer=False`` skips its first and last entry -- the
+    reference's weights load with strict=True, and the logits agree in eval() and train() mode, running statistics included."""
+    import numpy as np
+    data = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_models.npz"))
+    small = {"spec_conv_layers": [(6, 3, 3), (8, 5, 5), (8, 3, 3)], "spec_max_pooling": [(0, 2, 2), (2, 2, 2)],
+             "spec_dropout_rates": [], "spec_linear": [24, 12], "width": 16, "height": 16}
+    builds = {"conv_bn_affine": lambda: cfm.ConvolForwardNet(**small, useBatchNorm=True, useAffineTransformInBatchNorm=True),
+              "conv_bn": lambda: cfm.ConvolForwardNet(**small, useBatchNorm=True, useAffineTransformInBatchNorm=False),
+              "conv_plain": lambda: cfm.ConvolForwardNet(**small, useBatchNorm=False),
+              "wrn_10_1": lambda: Wide_ResNet(depth=10, widen_factor=1, dropout_rate=0.0, num_classes=10)}
+    for tag, build in builds.items():
+        m = build()
+        assert [n for n, _ in m.named_parameters()] == list(data[tag + "_param_names"]), tag
+        assert list(m.state_dict().keys()) == list(data[tag + "_state_names"]), tag
+        sd = {k: torch.from_numpy(data[f"{tag}_sd_{k}"].copy()) for k in data[tag + "_state_names"]}
+        m.load_state_dict(sd, strict=True)
+        x = torch.from_numpy(data[tag + "_x"])
+        m.eval()
+        with torch.no_grad():
+            y = m(x).numpy()
+        assert np.array_equal(y, data[tag + "_y_eval"]), (tag, float(np.abs(y - data[tag + "_y_eval"]).max()))
+        m.train()
+        with torch.no_grad():
+            y = m(x).numpy()
+        assert np.array_equal(y, data[tag + "_y_train"]), (tag, float(np.abs(y - data[tag + "_y_train"]).max()))
+        for k, v in m.state_dict().items():
+            if "running" in k or "num_batches" in k:
+                assert np.array_equal(v.numpy(), data[f"{tag}_after_{k}"]), (tag, k)
+    assert repr(cfm.teacherModelSpec) == str(data["teacherModelSpec"]) and repr(cfm.smallerModelSpec) == str(data["smallerModelSpec"])
